@@ -1,0 +1,154 @@
+/*
+ * som_b200.h — C ABI of the B200-native SOM-layer hot path.
+ *
+ * The reference (aluo7/ViT-SOM) has no FFI of its own: its hot path is the Python class
+ * `SOMLayer` (models/som_layer.py:8-152) calling ATen.  This header is the boundary a
+ * maintainer binds instead of those ATen calls.  Every entry point
+ *   - takes plain device pointers, sizes and a `cudaStream_t` passed as `void*`,
+ *   - never allocates, never synchronises the device, never owns memory,
+ *   - returns 0 on success and a negative code on failure; `som_last_error()` returns a
+ *     thread-local, human readable description of the last failure.
+ * All matrices are row-major fp32 with an explicit leading dimension in ELEMENTS.
+ *
+ * Reference call sites replaced (file:line in /root/reference):
+ *   som_prep_rows            F.normalize / the operand staging of cdist   models/som_layer.py:118-121
+ *   som_fwd_distances        torch.cdist(p=2) | 1 - mm(x̂, Ŵᵀ), argmin    models/som_layer.py:87-88,117-122
+ *   som_bmu_decode           torch.argmin result as int64                 models/som_layer.py:88
+ *   som_neighbourhood        compute_weights                              models/som_layer.py:144-152
+ *   som_weighted_loss        som_loss                                     models/som_layer.py:137-142
+ *   som_weighted_loss_grad   autograd MeanBackward0/MulBackward0          (autograd of :141-142)
+ *   som_bwd_coeffs           EuclideanDistBackward0 / Mm+NormalizeBackward (autograd of :118-122)
+ *   som_bwd_dx, som_bwd_dw   the two gradient GEMMs of the same backward
+ *
+ * Distance modes: 0 = euclidean (non-squared, ATen `_euclidean_dist` formula
+ * sqrt(clamp_min(|x|^2 - 2 x.w + |w|^2, 0))), 1 = cosine (1 - x̂.ŵ with F.normalize eps 1e-12).
+ * Manhattan (models/som_layer.py:115-116) is not a contraction and is out of scope.
+ */
+#ifndef SOM_B200_H_
+#define SOM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SOM_MODE_EUCLIDEAN 0
+#define SOM_MODE_COSINE    1
+
+#define SOM_OK             0
+#define SOM_ERR_ARG       -1   /* bad argument (null pointer, misalignment, unsupported size)   */
+#define SOM_ERR_CUDA      -2   /* a CUDA runtime / driver call failed                            */
+#define SOM_ERR_DEVICE    -3   /* device is not sm_100 (Blackwell B200) - there is no fallback   */
+
+/* ABI version, bumped on any signature change. */
+int som_b200_abi_version(void);
+
+/* Thread-local description of the last error returned on this thread ("" if none). */
+const char* som_last_error(void);
+
+/* Number of kernels this library has launched since load (or since the last reset). */
+int64_t som_launch_count(void);
+void    som_launch_count_reset(void);
+
+/*
+ * Operand staging.  For every row r < rows of src[rows, dim] (leading dimension ld_src):
+ *   mode 0: aux[r] = |src_r|^2,  v = src_r
+ *   mode 1: aux[r] = 1 / max(|src_r|, 1e-12),  v = src_r * aux[r]   (F.normalize)
+ * and writes the exact tf32 split hi = rn_tf32(v), lo = rn_tf32(v - hi) to hi/lo[rows, ld_out]
+ * (columns dim..ld_out-1 are zero filled).  ld_out must be a multiple of 4, hi/lo 16-byte aligned.
+ */
+int som_prep_rows(const float* src, int64_t rows, int64_t dim, int64_t ld_src, int mode,
+                  float* hi, float* lo, int64_t ld_out, float* aux, void* stream);
+
+/* packed[b] = INT64_MAX for b < B: must precede the first som_fwd_distances of a batch. */
+int som_bmu_init(long long* packed, int64_t B, void* stream);
+
+/*
+ * Pairwise distances + best-matching-unit search (fused tcgen05 3xTF32 GEMM + epilogue).
+ *   x_hi/x_lo [B, ldx], w_hi/w_lo [K, ldw] : staged operands from som_prep_rows (same mode)
+ *   x_aux [B], w_aux [K]                   : aux vectors from som_prep_rows (unused for cosine)
+ *   dist [B, ldd]                          : out, distances (may be NULL: BMU-only fast path)
+ *   packed [B]                             : in/out, per-row min of (ordered(key) << 32 | k + idx_offset),
+ *                                            key = squared distance (euclidean) or distance (cosine);
+ *                                            combining shards = elementwise signed-int64 min.
+ * idx_offset lets a rank that owns prototypes [idx_offset, idx_offset + K) emit global indices.
+ */
+int som_fwd_distances(const float* x_hi, const float* x_lo, int64_t ldx, const float* x_aux,
+                      const float* w_hi, const float* w_lo, int64_t ldw, const float* w_aux,
+                      int64_t B, int64_t K, int64_t D, int mode, int64_t idx_offset,
+                      float* dist, int64_t ldd, long long* packed, void* stream);
+
+/* bmu[b] = low 32 bits of packed[b] (clamped to [0, K_total)), optional min_key[b] = winning key. */
+int som_bmu_decode(const long long* packed, int64_t B, int64_t K_total,
+                   int64_t* bmu, float* min_key, void* stream);
+
+/*
+ * Gaussian neighbourhood weights w[b,k] = exp(-|p_k - p_bmu(b)|^2 / (2 T^2)), materialised.
+ *   grid_pos [K_total, 2] fp32 (models/som_layer.py:60-81); rows k_offset..k_offset+K are produced.
+ *   T_dev : device pointer to the current temperature (fp32).
+ */
+int som_neighbourhood(const int64_t* bmu, const float* grid_pos, int64_t B, int64_t K,
+                      int64_t k_offset, const float* T_dev, float* w, int64_t ldw, void* stream);
+
+/*
+ * loss = inv_count * sum_{b,k} w[b,k] * dist[b,k] with w recomputed on the fly (never stored).
+ *   partials : device scratch, at least som_loss_scratch_floats(B, K) floats + 1 counter word,
+ *              zero-initialised once (the kernel restores the zero state itself).
+ *   inv_count: 1 / (B_global * K_global) (mean over the full matrix, models/som_layer.py:142).
+ */
+int64_t som_loss_scratch_floats(int64_t B, int64_t K);
+int som_weighted_loss(const float* dist, int64_t ldd, const int64_t* bmu, const float* grid_pos,
+                      int64_t B, int64_t K, int64_t k_offset, const float* T_dev, float inv_count,
+                      float* partials, float* loss_out, void* stream);
+
+/* G[b,k] = g_out * inv_count * w[b,k]  (upstream gradient of the distances). g_out_dev: device scalar. */
+int som_weighted_loss_grad(const int64_t* bmu, const float* grid_pos, int64_t B, int64_t K,
+                           int64_t k_offset, const float* T_dev, const float* g_out_dev,
+                           float inv_count, float* G, int64_t ldg, void* stream);
+
+/*
+ * Backward staging: from the upstream gradient G[B,K] of the distances build the GEMM operand
+ * R (tf32 hi/lo split, [B, ldr]) and the rank-1 coefficients of the closed-form backward
+ *   euclidean: R = G / dist (0 where dist == 0);  ax[b] = sum_k R, bx = 1;  aw[k] = sum_b R, bw = 1
+ *   cosine   : R = G;  c_b = sum_k G (1 - dist), ax = x_aux^2 c_b, bx = x_aux;  same for w.
+ * so that  dx = ax * x - bx * (R  . W~)   and   dw = aw * w - bw * (R^T . x~)
+ * with W~/x~ the staged (normalised for cosine) operands.  ax, aw must be zero on entry.
+ */
+int som_bwd_coeffs(const float* G, int64_t ldg, const float* dist, int64_t ldd,
+                   int64_t B, int64_t K, int mode, const float* x_aux, const float* w_aux,
+                   float* r_hi, float* r_lo, int64_t ldr,
+                   float* ax, float* bx, float* aw, float* bw, void* stream);
+
+/* dx[B,D] = ax[b] * x[b,:] - bx[b] * sum_k R[b,k] W~[k,:]   (W~ read MN-major, no transpose copy). */
+int som_bwd_dx(const float* r_hi, const float* r_lo, int64_t ldr,
+               const float* w_hi, const float* w_lo, int64_t ldw,
+               const float* x, int64_t ldx, const float* ax, const float* bx,
+               int64_t B, int64_t K, int64_t D, float* dx, int64_t lddx, void* stream);
+
+/* dw[K,D] = aw[k] * w[k,:] - bw[k] * sum_b R[b,k] x~[b,:]   (R and x~ read MN-major). */
+int som_bwd_dw(const float* r_hi, const float* r_lo, int64_t ldr,
+               const float* x_hi, const float* x_lo, int64_t ldx,
+               const float* w, int64_t ldw, const float* aw, const float* bw,
+               int64_t B, int64_t K, int64_t D, float* dw, int64_t lddw, void* stream);
+
+/*
+ * Diagnostic entry point (used by the tests to validate the tensor-core mainloop in isolation):
+ * C[M,N] = A . B^T in 3xTF32 with A = a_hi + a_lo, B = b_hi + b_lo.
+ *   a_mn = 0: A stored [M, Kred] (K-major)    a_mn = 1: A stored [Kred, M] (MN-major)
+ *   b_mn = 0: B stored [N, Kred] (K-major)    b_mn = 1: B stored [Kred, N] (MN-major)
+ *   bn: tile width (16, 32, 64, 96 or 128; 0 = auto), kchunk: k-blocks (of 32) per tensor-core
+ *   accumulation chunk (0 = default), passes: 3 = 3xTF32, 1 = hi*hi only.
+ */
+int som_debug_gemm(const float* a_hi, const float* a_lo, int64_t lda, int a_mn,
+                   const float* b_hi, const float* b_lo, int64_t ldb, int b_mn,
+                   int64_t M, int64_t N, int64_t Kred, int bn, int kchunk, int passes,
+                   float* C, int64_t ldc, void* stream);
+
+/* Tuning knobs (process-wide): tile width override (0 = auto) and k-blocks per accumulation chunk. */
+void som_set_tuning(int bn_override, int kchunk);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* SOM_B200_H_ */

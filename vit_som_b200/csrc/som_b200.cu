@@ -1,0 +1,604 @@
+// som_b200.cu — C-ABI library of the B200-native SOM-layer hot path (see include/som_b200.h).
+//
+// Kernels in this translation unit (all sm_100a):
+//   som_gemm3x_kernel<EPI_DIST|EPI_GRAD|EPI_RAW>  tcgen05/TMA 3xTF32 GEMM + fused epilogue (som_gemm.cuh)
+//   prep_rows_kernel        operand staging: row norms (+ F.normalize) and exact tf32 hi/lo split
+//   bmu_init/decode         packed (key,index) <-> int64 BMU
+//   neighbourhood_kernel    Gaussian grid weights, materialised on demand     (models/som_layer.py:144-152)
+//   weighted_loss_kernel    mean(w * d) with w recomputed in registers        (models/som_layer.py:137-142)
+//   loss_grad_kernel        G = g_out * w / (B K)
+//   bwd_coeffs_kernel       R = G / d (masked), rank-1 coefficients           (ATen _euclidean_dist_backward)
+//
+// There is no CPU path and no fallback: on anything that is not compute capability 10.x every
+// entry point fails with SOM_ERR_DEVICE.
+#include "../../include/som_b200.h"
+#include "som_gemm.cuh"
+
+#include <cudaTypedefs.h>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<int64_t> g_launches{0};
+std::atomic<int> g_bn_override{0};
+std::atomic<int> g_kchunk{16};
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+#define SOM_CUDA(call)                                                                              \
+  do {                                                                                              \
+    cudaError_t err__ = (call);                                                                     \
+    if (err__ != cudaSuccess)                                                                       \
+      return fail(SOM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__));             \
+  } while (0)
+
+struct DeviceInfo { int sms = 0; int cc_major = 0; bool ok = false; };
+
+int device_info(DeviceInfo& out) {
+  static thread_local int cached_dev = -1;
+  static thread_local DeviceInfo cached;
+  int dev = 0;
+  SOM_CUDA(cudaGetDevice(&dev));
+  if (dev != cached_dev) {
+    DeviceInfo d;
+    SOM_CUDA(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
+    SOM_CUDA(cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    d.ok = true;
+    cached = d;
+    cached_dev = dev;
+  }
+  out = cached;
+  if (out.cc_major != 10)
+    return fail(SOM_ERR_DEVICE, "som_b200 needs a compute-capability 10.x GPU (B200, sm_100a); found major " +
+                                    std::to_string(out.cc_major) + " - there is no fallback path");
+  return SOM_OK;
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor map: `inner` contiguous elements per row, `outer` rows, row pitch ld elements,
+// box = 32 x box_outer, zero fill outside the tensor.  K-major operands use the 128-byte swizzle with 16-byte
+// atoms; MN-major tf32 operands need the 32-byte-atom variant (matches UMMA SWIZZLE_128B_BASE32B).
+int make_tmap(CUtensorMap* map, const float* ptr, int64_t inner, int64_t outer, int64_t ld, int box_outer,
+              bool mn_major = false) {
+  auto enc = get_encode();
+  if (!enc) return fail(SOM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld & 3) != 0)
+    return fail(SOM_ERR_ARG, "TMA operand must be 16-byte aligned with a leading dimension that is a multiple of 4");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
+  cuuint32_t box[2] = {32u, static_cast<cuuint32_t>(box_outer)};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SOM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(r));
+  return SOM_OK;
+}
+
+int pick_bn(int64_t M, int64_t N, int sms, int b_mn) {
+  const int forced = g_bn_override.load();
+  if (forced) return forced;
+  if (N <= 16 && !b_mn) return 16;
+  const int cands[4] = {128, 96, 64, 32};
+  const int64_t tm = (M + som::BM - 1) / som::BM;
+  int best = 128;
+  double best_cost = 1e30;
+  for (int bn : cands) {
+    const int64_t tiles = tm * ((N + bn - 1) / bn);
+    const int64_t waves = (tiles + sms - 1) / sms;
+    const double cost = static_cast<double>(waves) * (bn + 24);   // MMA time ~ bn, fixed per-tile overhead
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+template <int EPI>
+int launch_gemm_t(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi,
+                  const CUtensorMap& tb_lo, const som::GemmShape& g, const som::EpiParams& e, int grid,
+                  size_t smem, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SOM_CUDA(cudaFuncSetAttribute(som::som_gemm3x_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  som::SMEM_LIMIT));
+    attr_set = true;
+  }
+  som::som_gemm3x_kernel<EPI><<<grid, som::NUM_THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, g, e);
+  SOM_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return SOM_OK;
+}
+
+int launch_gemm(int epi, const float* a_hi, const float* a_lo, int64_t lda, int a_mn, const float* b_hi,
+                const float* b_lo, int64_t ldb, int b_mn, int64_t M, int64_t N, int64_t Kred, int bn_req,
+                int kchunk_req, int passes, const som::EpiParams& e, cudaStream_t st) {
+  DeviceInfo di;
+  if (int rc = device_info(di)) return rc;
+  if (M <= 0 || N <= 0 || Kred <= 0) return fail(SOM_ERR_ARG, "GEMM dimensions must be positive");
+  if (M > (1ll << 30) || N > (1ll << 30) || Kred > (1ll << 30)) return fail(SOM_ERR_ARG, "GEMM dimension too large");
+  if (!a_hi || !b_hi || (passes == 3 && (!a_lo || !b_lo))) return fail(SOM_ERR_ARG, "null GEMM operand");
+  if (passes != 1 && passes != 3) return fail(SOM_ERR_ARG, "passes must be 1 or 3");
+  int bn = bn_req > 0 ? bn_req : pick_bn(M, N, di.sms, b_mn);
+  if (bn % 16 != 0 || bn < 16 || bn > som::MAX_BN) return fail(SOM_ERR_ARG, "tile width must be a multiple of 16 in [16,128]");
+
+  som::GemmShape g;
+  g.M = static_cast<int>(M); g.N = static_cast<int>(N); g.Kred = static_cast<int>(Kred);
+  g.bn = bn; g.a_mn = a_mn ? 1 : 0; g.b_mn = b_mn ? 1 : 0;
+  g.kchunk = kchunk_req > 0 ? kchunk_req : g_kchunk.load();
+  g.passes = passes;
+  g.tiles_m = static_cast<int>((M + som::BM - 1) / som::BM);
+  g.tiles_n = static_cast<int>((N + bn - 1) / bn);
+  const size_t b_tile = g.b_mn ? static_cast<size_t>((bn + 31) / 32) * som::PANEL_BYTES : static_cast<size_t>(bn) * som::BK * 4;
+  const size_t stage = 2 * som::A_TILE_BYTES + 2 * b_tile;
+  const size_t fixed = 1024 /*alignment slack*/ + 8 * (2 * som::MAX_STAGES + 4) + 16;
+  int nst = static_cast<int>((som::SMEM_LIMIT - fixed) / stage);
+  if (nst > som::MAX_STAGES) nst = som::MAX_STAGES;
+  if (nst < 2) return fail(SOM_ERR_ARG, "tile does not fit shared memory");
+  g.nstages = nst;
+  const size_t smem = fixed + nst * stage;
+
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  int rc;
+  if (g.a_mn) { if ((rc = make_tmap(&ta_hi, a_hi, M, Kred, lda, 32, true))) return rc; if ((rc = make_tmap(&ta_lo, a_lo ? a_lo : a_hi, M, Kred, lda, 32, true))) return rc; }
+  else        { if ((rc = make_tmap(&ta_hi, a_hi, Kred, M, lda, som::BM))) return rc; if ((rc = make_tmap(&ta_lo, a_lo ? a_lo : a_hi, Kred, M, lda, som::BM))) return rc; }
+  if (g.b_mn) { if ((rc = make_tmap(&tb_hi, b_hi, N, Kred, ldb, 32, true))) return rc; if ((rc = make_tmap(&tb_lo, b_lo ? b_lo : b_hi, N, Kred, ldb, 32, true))) return rc; }
+  else        { if ((rc = make_tmap(&tb_hi, b_hi, Kred, N, ldb, bn))) return rc; if ((rc = make_tmap(&tb_lo, b_lo ? b_lo : b_hi, Kred, N, ldb, bn))) return rc; }
+
+  const int64_t nwork = static_cast<int64_t>(g.tiles_m) * g.tiles_n;
+  const int grid = static_cast<int>(nwork < di.sms ? nwork : di.sms);
+  switch (epi) {
+    case som::EPI_RAW:  return launch_gemm_t<som::EPI_RAW>(ta_hi, ta_lo, tb_hi, tb_lo, g, e, grid, smem, st);
+    case som::EPI_DIST: return launch_gemm_t<som::EPI_DIST>(ta_hi, ta_lo, tb_hi, tb_lo, g, e, grid, smem, st);
+    case som::EPI_GRAD: return launch_gemm_t<som::EPI_GRAD>(ta_hi, ta_lo, tb_hi, tb_lo, g, e, grid, smem, st);
+  }
+  return fail(SOM_ERR_ARG, "unknown epilogue");
+}
+
+// ----------------------------------------------------------------------------------------------
+// Elementwise / reduction kernels around the GEMMs
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// GROUP threads cooperate on one row (GROUP = 32: warp per row, GROUP = 256: block per row).
+template <int GROUP>
+__global__ void __launch_bounds__(256)
+prep_rows_kernel(const float* __restrict__ src, long long rows, int dim, long long ld_src, int mode,
+                 float* __restrict__ hi, float* __restrict__ lo, long long ld_out, float* __restrict__ aux) {
+  constexpr int ROWS_PER_BLOCK = 256 / GROUP;
+  const int gi = threadIdx.x / GROUP, gt = threadIdx.x % GROUP;
+  const long long row = static_cast<long long>(blockIdx.x) * ROWS_PER_BLOCK + gi;
+  __shared__ float red[8];
+  const bool active = row < rows;
+  const float* p = src + (active ? row : 0) * ld_src;
+  const bool vec = (dim & 3) == 0 && (ld_src & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+
+  float ss = 0.f;
+  if (active) {
+    if (vec) {
+      for (int i = gt * 4; i < dim; i += GROUP * 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p + i));
+        ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+      }
+    } else {
+      for (int i = gt; i < dim; i += GROUP) { const float v = __ldg(p + i); ss = fmaf(v, v, ss); }
+    }
+  }
+  ss = warp_sum(ss);
+  if constexpr (GROUP == 256) {
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ss += red[i];
+  }
+  if (!active) return;
+  float denom = 1.f;
+  if (mode == 1) {
+    denom = fmaxf(sqrtf(ss), 1e-12f);            // F.normalize(p=2, eps=1e-12)
+    if (gt == 0) aux[row] = 1.f / denom;
+  } else if (gt == 0) {
+    aux[row] = ss;
+  }
+  float* ph = hi + row * ld_out;
+  float* pl = lo + row * ld_out;
+  const int dim_out = static_cast<int>(ld_out);
+  if (vec) {
+    for (int i = gt * 4; i < dim_out; i += GROUP * 4) {
+      float4 h = make_float4(0.f, 0.f, 0.f, 0.f), l = h;
+      if (i < dim) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(p + i));
+        if (mode == 1) { v.x = v.x / denom; v.y = v.y / denom; v.z = v.z / denom; v.w = v.w / denom; }
+        h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+        l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+      }
+      *reinterpret_cast<float4*>(ph + i) = h;
+      *reinterpret_cast<float4*>(pl + i) = l;
+    }
+  } else {
+    for (int i = gt; i < dim_out; i += GROUP) {
+      float h = 0.f, l = 0.f;
+      if (i < dim) {
+        float v = __ldg(p + i);
+        if (mode == 1) v = v / denom;
+        h = tf32_rna(v);
+        l = tf32_rna(v - h);
+      }
+      ph[i] = h;
+      pl[i] = l;
+    }
+  }
+}
+
+__global__ void bmu_init_kernel(long long* packed, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) packed[i] = 0x7fffffffffffffffLL;
+}
+
+__global__ void bmu_decode_kernel(const long long* __restrict__ packed, long long n, long long k_total,
+                                  long long* __restrict__ bmu, float* __restrict__ min_key) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long p = packed[i];
+  long long idx = p & 0xffffffffLL;
+  if (idx >= k_total) idx = 0;                    // NaN / all-inf rows: stay in bounds
+  bmu[i] = idx;
+  if (min_key) {
+    int k = static_cast<int>(p >> 32);
+    k ^= (k >> 31) & 0x7fffffff;
+    min_key[i] = __int_as_float(k);
+  }
+}
+
+// w = exp(-|p_k - p_bmu|^2 / (2 T^2)), written the way the reference evaluates it:
+// norm first, then square, divide, exp (models/som_layer.py:149-150).
+__device__ __forceinline__ float neighbourhood_weight(float pky, float pkx, float pby, float pbx, float two_t2) {
+  const float dy = pky - pby, dx = pkx - pbx;
+  const float dist = sqrtf(dy * dy + dx * dx);
+  return expf(-(dist * dist) / two_t2);
+}
+
+constexpr int COLS_PER_BLOCK = 1024;   // 256 threads x 4 columns
+
+__global__ void __launch_bounds__(256)
+neighbourhood_kernel(const long long* __restrict__ bmu, const float* __restrict__ pos, long long K, long long k_offset,
+                     const float* __restrict__ T_dev, float* __restrict__ w, long long ldw) {
+  const long long b = blockIdx.x;
+  const float T = __ldg(T_dev);
+  const float two_t2 = 2.f * (T * T);
+  const long long bi = bmu[b];
+  const float pby = __ldg(pos + 2 * bi), pbx = __ldg(pos + 2 * bi + 1);
+  for (int i = 0; i < 4; ++i) {
+    const long long k = static_cast<long long>(blockIdx.y) * COLS_PER_BLOCK + i * 256 + threadIdx.x;
+    if (k < K) {
+      const float2 pk = __ldg(reinterpret_cast<const float2*>(pos) + k_offset + k);
+      w[b * ldw + k] = neighbourhood_weight(pk.x, pk.y, pby, pbx, two_t2);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+weighted_loss_kernel(const float* __restrict__ dist, long long ldd, const long long* __restrict__ bmu,
+                     const float* __restrict__ pos, long long K, long long k_offset, const float* __restrict__ T_dev,
+                     float inv_count, float* __restrict__ partials, float* __restrict__ loss_out) {
+  const long long b = blockIdx.x;
+  const float T = __ldg(T_dev);
+  const float two_t2 = 2.f * (T * T);
+  const long long bi = bmu[b];
+  const float pby = __ldg(pos + 2 * bi), pbx = __ldg(pos + 2 * bi + 1);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long k = static_cast<long long>(blockIdx.y) * COLS_PER_BLOCK + i * 256 + threadIdx.x;
+    if (k < K) {
+      const float2 pk = __ldg(reinterpret_cast<const float2*>(pos) + k_offset + k);
+      s = fmaf(neighbourhood_weight(pk.x, pk.y, pby, pbx, two_t2), __ldg(dist + b * ldd + k), s);
+    }
+  }
+  __shared__ float red[8];
+  __shared__ double dred[256];
+  __shared__ bool is_last;
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  const long long nblocks = static_cast<long long>(gridDim.x) * gridDim.y;
+  unsigned int* counter = reinterpret_cast<unsigned int*>(partials + nblocks);
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i];
+    partials[static_cast<long long>(blockIdx.y) * gridDim.x + blockIdx.x] = t;
+    __threadfence();
+    const unsigned int done = atomicAdd(counter, 1u);
+    is_last = (done == nblocks - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  // Last block: fixed-order fp64 reduction of all partials -> deterministic loss.
+  __threadfence();
+  double acc = 0.0;
+  for (long long i = threadIdx.x; i < nblocks; i += 256) acc += static_cast<double>(__ldcg(partials + i));
+  dred[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) dred[threadIdx.x] += dred[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    *loss_out = static_cast<float>(dred[0] * static_cast<double>(inv_count));
+    *counter = 0u;                                   // restore the zero state for the next call
+  }
+}
+
+__global__ void __launch_bounds__(256)
+loss_grad_kernel(const long long* __restrict__ bmu, const float* __restrict__ pos, long long K, long long k_offset,
+                 const float* __restrict__ T_dev, const float* __restrict__ g_out, float inv_count,
+                 float* __restrict__ G, long long ldg) {
+  const long long b = blockIdx.x;
+  const float T = __ldg(T_dev);
+  const float two_t2 = 2.f * (T * T);
+  const float scale = __ldg(g_out) * inv_count;
+  const long long bi = bmu[b];
+  const float pby = __ldg(pos + 2 * bi), pbx = __ldg(pos + 2 * bi + 1);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long k = static_cast<long long>(blockIdx.y) * COLS_PER_BLOCK + i * 256 + threadIdx.x;
+    if (k < K) {
+      const float2 pk = __ldg(reinterpret_cast<const float2*>(pos) + k_offset + k);
+      G[b * ldg + k] = scale * neighbourhood_weight(pk.x, pk.y, pby, pbx, two_t2);
+    }
+  }
+}
+
+constexpr int COEFF_ROWS = 32;
+
+// thread <-> column k, loop over COEFF_ROWS rows: coalesced reads of G/dist, coalesced writes of R.
+__global__ void __launch_bounds__(256)
+bwd_coeffs_kernel(const float* __restrict__ G, long long ldg, const float* __restrict__ dist, long long ldd,
+                  long long B, long long K, int mode, const float* __restrict__ x_aux, const float* __restrict__ w_aux,
+                  float* __restrict__ r_hi, float* __restrict__ r_lo, long long ldr,
+                  float* __restrict__ ax, float* __restrict__ bx, float* __restrict__ aw, float* __restrict__ bw) {
+  const long long k = static_cast<long long>(blockIdx.y) * 256 + threadIdx.x;
+  const long long b0 = static_cast<long long>(blockIdx.x) * COEFF_ROWS;
+  const bool col_ok = k < K;
+  __shared__ float red[COEFF_ROWS][8];
+  float colsum = 0.f;
+#pragma unroll 4
+  for (int r = 0; r < COEFF_ROWS; ++r) {
+    const long long b = b0 + r;
+    float rowterm = 0.f;
+    if (b < B && col_ok) {
+      const float g = __ldg(G + b * ldg + k);
+      const float d = __ldg(dist + b * ldd + k);
+      float rv, term;
+      if (mode == 0) {
+        rv = (d == 0.f) ? 0.f : g / d;               // ATen: ratio.masked_fill_(dist == 0, 0)
+        term = rv;
+      } else {
+        rv = g;
+        term = g * (1.f - d);                        // g * (x̂ . ŵ): projection coefficient of normalize backward
+      }
+      const float h = tf32_rna(rv);
+      r_hi[b * ldr + k] = h;
+      r_lo[b * ldr + k] = tf32_rna(rv - h);
+      colsum += term;
+      rowterm = term;
+    }
+    rowterm = warp_sum(rowterm);
+    if ((threadIdx.x & 31) == 0) red[r][threadIdx.x >> 5] = rowterm;
+  }
+  __syncthreads();
+  if (threadIdx.x < COEFF_ROWS) {
+    const long long b = b0 + threadIdx.x;
+    if (b < B) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += red[threadIdx.x][i];
+      const float xa = (mode == 1) ? __ldg(x_aux + b) : 1.f;
+      atomicAdd(ax + b, (mode == 1) ? xa * xa * t : t);
+      if (blockIdx.y == 0) bx[b] = xa;
+    }
+  }
+  if (col_ok) {
+    const float wa = (mode == 1) ? __ldg(w_aux + k) : 1.f;
+    atomicAdd(aw + k, (mode == 1) ? wa * wa * colsum : colsum);
+    if (blockIdx.x == 0) bw[k] = wa;
+  }
+}
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int som_b200_abi_version(void) { return 1; }
+const char* som_last_error(void) { return g_last_error.c_str(); }
+int64_t som_launch_count(void) { return g_launches.load(); }
+void som_launch_count_reset(void) { g_launches.store(0); }
+void som_set_tuning(int bn_override, int kchunk) {
+  g_bn_override.store(bn_override);
+  if (kchunk > 0) g_kchunk.store(kchunk);
+}
+
+int som_prep_rows(const float* src, int64_t rows, int64_t dim, int64_t ld_src, int mode, float* hi, float* lo,
+                  int64_t ld_out, float* aux, void* stream) {
+  DeviceInfo di;
+  if (int rc = device_info(di)) return rc;
+  if (!src || !hi || !lo || !aux) return fail(SOM_ERR_ARG, "som_prep_rows: null pointer");
+  if (rows <= 0 || dim <= 0 || dim > (1ll << 30) || ld_src < dim || ld_out < dim)
+    return fail(SOM_ERR_ARG, "som_prep_rows: bad shape");
+  if ((ld_out & 3) != 0 || ((reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 15) != 0)
+    return fail(SOM_ERR_ARG, "som_prep_rows: hi/lo must be 16-byte aligned with ld_out % 4 == 0");
+  if (mode != SOM_MODE_EUCLIDEAN && mode != SOM_MODE_COSINE) return fail(SOM_ERR_ARG, "som_prep_rows: bad mode");
+  if (dim <= 1024) {
+    prep_rows_kernel<32><<<static_cast<unsigned>((rows + 7) / 8), 256, 0, as_stream(stream)>>>(
+        src, rows, static_cast<int>(dim), ld_src, mode, hi, lo, ld_out, aux);
+  } else {
+    prep_rows_kernel<256><<<static_cast<unsigned>(rows), 256, 0, as_stream(stream)>>>(
+        src, rows, static_cast<int>(dim), ld_src, mode, hi, lo, ld_out, aux);
+  }
+  SOM_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return SOM_OK;
+}
+
+int som_bmu_init(long long* packed, int64_t B, void* stream) {
+  DeviceInfo di;
+  if (int rc = device_info(di)) return rc;
+  if (!packed || B <= 0) return fail(SOM_ERR_ARG, "som_bmu_init: bad argument");
+  bmu_init_kernel<<<static_cast<unsigned>((B + 255) / 256), 256, 0, as_stream(stream)>>>(packed, B);
+  SOM_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return SOM_OK;
+}
+
+int som_fwd_distances(const float* x_hi, const float* x_lo, int64_t ldx, const float* x_aux, const float* w_hi,
+                      const float* w_lo, int64_t ldw, const float* w_aux, int64_t B, int64_t K, int64_t D, int mode,
+                      int64_t idx_offset, float* dist, int64_t ldd, long long* packed, void* stream) {
+  if (!packed) return fail(SOM_ERR_ARG, "som_fwd_distances: packed must not be null");
+  if (mode != SOM_MODE_EUCLIDEAN && mode != SOM_MODE_COSINE) return fail(SOM_ERR_ARG, "som_fwd_distances: bad mode");
+  if (mode == SOM_MODE_EUCLIDEAN && (!x_aux || !w_aux)) return fail(SOM_ERR_ARG, "som_fwd_distances: norms required");
+  if (dist && ldd < K) return fail(SOM_ERR_ARG, "som_fwd_distances: ldd < K");
+  if (idx_offset < 0 || idx_offset + K > 0x7fffffffLL) return fail(SOM_ERR_ARG, "som_fwd_distances: index range");
+  som::EpiParams e{};
+  e.row_aux = x_aux; e.col_aux = w_aux; e.dist = dist; e.ldd = ldd; e.packed = packed;
+  e.idx_offset = static_cast<int>(idx_offset); e.mode = mode;
+  return launch_gemm(som::EPI_DIST, x_hi, x_lo, ldx, 0, w_hi, w_lo, ldw, 0, B, K, D, 0, 0, 3, e, as_stream(stream));
+}
+
+int som_bmu_decode(const long long* packed, int64_t B, int64_t K_total, int64_t* bmu, float* min_key, void* stream) {
+  DeviceInfo di;
+  if (int rc = device_info(di)) return rc;
+  if (!packed || !bmu || B <= 0 || K_total <= 0) return fail(SOM_ERR_ARG, "som_bmu_decode: bad argument");
+  bmu_decode_kernel<<<static_cast<unsigned>((B + 255) / 256), 256, 0, as_stream(stream)>>>(
+      packed, B, K_total, reinterpret_cast<long long*>(bmu), min_key);
+  SOM_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return SOM_OK;
+}
+
+int som_neighbourhood(const int64_t* bmu, const float* grid_pos, int64_t B, int64_t K, int64_t k_offset,
+                      const float* T_dev, float* w, int64_t ldw, void* stream) {
+  DeviceInfo di;
+  if (int rc = device_info(di)) return rc;
+  if (!bmu || !grid_pos || !T_dev || !w || B <= 0 || K <= 0 || ldw < K)
+    return fail(SOM_ERR_ARG, "som_neighbourhood: bad argument");
+  dim3 grid(static_cast<unsigned>(B), static_cast<unsigned>((K + COLS_PER_BLOCK - 1) / COLS_PER_BLOCK));
+  neighbourhood_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const long long*>(bmu), grid_pos, K,
+                                                           k_offset, T_dev, w, ldw);
+  SOM_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return SOM_OK;
+}
+
+int64_t som_loss_scratch_floats(int64_t B, int64_t K) {
+  return B * ((K + COLS_PER_BLOCK - 1) / COLS_PER_BLOCK) + 2;
+}
+
+int som_weighted_loss(const float* dist, int64_t ldd, const int64_t* bmu, const float* grid_pos, int64_t B, int64_t K,
+                      int64_t k_offset, const float* T_dev, float inv_count, float* partials, float* loss_out,
+                      void* stream) {
+  DeviceInfo di;
+  if (int rc = device_info(di)) return rc;
+  if (!dist || !bmu || !grid_pos || !T_dev || !partials || !loss_out || B <= 0 || K <= 0 || ldd < K)
+    return fail(SOM_ERR_ARG, "som_weighted_loss: bad argument");
+  dim3 grid(static_cast<unsigned>(B), static_cast<unsigned>((K + COLS_PER_BLOCK - 1) / COLS_PER_BLOCK));
+  weighted_loss_kernel<<<grid, 256, 0, as_stream(stream)>>>(dist, ldd, reinterpret_cast<const long long*>(bmu),
+                                                           grid_pos, K, k_offset, T_dev, inv_count, partials, loss_out);
+  SOM_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return SOM_OK;
+}
+
+int som_weighted_loss_grad(const int64_t* bmu, const float* grid_pos, int64_t B, int64_t K, int64_t k_offset,
+                           const float* T_dev, const float* g_out_dev, float inv_count, float* G, int64_t ldg,
+                           void* stream) {
+  DeviceInfo di;
+  if (int rc = device_info(di)) return rc;
+  if (!bmu || !grid_pos || !T_dev || !g_out_dev || !G || B <= 0 || K <= 0 || ldg < K)
+    return fail(SOM_ERR_ARG, "som_weighted_loss_grad: bad argument");
+  dim3 grid(static_cast<unsigned>(B), static_cast<unsigned>((K + COLS_PER_BLOCK - 1) / COLS_PER_BLOCK));
+  loss_grad_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const long long*>(bmu), grid_pos, K, k_offset,
+                                                       T_dev, g_out_dev, inv_count, G, ldg);
+  SOM_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return SOM_OK;
+}
+
+int som_bwd_coeffs(const float* G, int64_t ldg, const float* dist, int64_t ldd, int64_t B, int64_t K, int mode,
+                   const float* x_aux, const float* w_aux, float* r_hi, float* r_lo, int64_t ldr, float* ax, float* bx,
+                   float* aw, float* bw, void* stream) {
+  DeviceInfo di;
+  if (int rc = device_info(di)) return rc;
+  if (!G || !dist || !r_hi || !r_lo || !ax || !bx || !aw || !bw || B <= 0 || K <= 0 || ldg < K || ldd < K || ldr < K)
+    return fail(SOM_ERR_ARG, "som_bwd_coeffs: bad argument");
+  if (mode == SOM_MODE_COSINE && (!x_aux || !w_aux)) return fail(SOM_ERR_ARG, "som_bwd_coeffs: cosine needs the reciprocal norms");
+  if (mode != SOM_MODE_EUCLIDEAN && mode != SOM_MODE_COSINE) return fail(SOM_ERR_ARG, "som_bwd_coeffs: bad mode");
+  dim3 grid(static_cast<unsigned>((B + COEFF_ROWS - 1) / COEFF_ROWS), static_cast<unsigned>((K + 255) / 256));
+  bwd_coeffs_kernel<<<grid, 256, 0, as_stream(stream)>>>(G, ldg, dist, ldd, B, K, mode, x_aux, w_aux, r_hi, r_lo, ldr,
+                                                        ax, bx, aw, bw);
+  SOM_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return SOM_OK;
+}
+
+int som_bwd_dx(const float* r_hi, const float* r_lo, int64_t ldr, const float* w_hi, const float* w_lo, int64_t ldw,
+               const float* x, int64_t ldx, const float* ax, const float* bx, int64_t B, int64_t K, int64_t D,
+               float* dx, int64_t lddx, void* stream) {
+  if (!x || !ax || !bx || !dx || ldx < D || lddx < D) return fail(SOM_ERR_ARG, "som_bwd_dx: bad argument");
+  som::EpiParams e{};
+  e.alpha = ax; e.beta = bx; e.src = x; e.lds = ldx; e.out = dx; e.ldo = lddx;
+  // C[B,D] = R[B,K] . W[K,D]: A = R K-major (reduction K contiguous), B = W MN-major (D contiguous)
+  return launch_gemm(som::EPI_GRAD, r_hi, r_lo, ldr, 0, w_hi, w_lo, ldw, 1, B, D, K, 0, 0, 3, e, as_stream(stream));
+}
+
+int som_bwd_dw(const float* r_hi, const float* r_lo, int64_t ldr, const float* x_hi, const float* x_lo, int64_t ldx,
+               const float* w, int64_t ldw, const float* aw, const float* bw, int64_t B, int64_t K, int64_t D,
+               float* dw, int64_t lddw, void* stream) {
+  if (!w || !aw || !bw || !dw || ldw < D || lddw < D) return fail(SOM_ERR_ARG, "som_bwd_dw: bad argument");
+  som::EpiParams e{};
+  e.alpha = aw; e.beta = bw; e.src = w; e.lds = ldw; e.out = dw; e.ldo = lddw;
+  // C[K,D] = R^T[K,B] . x[B,D]: A = R read MN-major (K contiguous), B = x MN-major (D contiguous)
+  return launch_gemm(som::EPI_GRAD, r_hi, r_lo, ldr, 1, x_hi, x_lo, ldx, 1, K, D, B, 0, 0, 3, e, as_stream(stream));
+}
+
+int som_debug_gemm(const float* a_hi, const float* a_lo, int64_t lda, int a_mn, const float* b_hi, const float* b_lo,
+                   int64_t ldb, int b_mn, int64_t M, int64_t N, int64_t Kred, int bn, int kchunk, int passes, float* C,
+                   int64_t ldc, void* stream) {
+  if (!C || ldc < N) return fail(SOM_ERR_ARG, "som_debug_gemm: bad output");
+  som::EpiParams e{};
+  e.out = C; e.ldo = ldc;
+  return launch_gemm(som::EPI_RAW, a_hi, a_lo, lda, a_mn, b_hi, b_lo, ldb, b_mn, M, N, Kred, bn, kchunk, passes, e,
+                     as_stream(stream));
+}
+
+}  // extern "C"
