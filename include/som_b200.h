@@ -93,8 +93,9 @@ int som_neighbourhood(const int64_t* bmu, const float* grid_pos, int64_t B, int6
 
 /*
  * loss = inv_count * sum_{b,k} w[b,k] * dist[b,k] with w recomputed on the fly (never stored).
- *   partials : device scratch, at least som_loss_scratch_floats(B, K) floats + 1 counter word,
- *              zero-initialised once (the kernel restores the zero state itself).
+ *   partials : device scratch of at least som_loss_scratch_floats(B, K) floats; word 0 is a completion
+ *              counter that must be zero on entry (zero the buffer once; the kernel restores the zero
+ *              state itself), so one buffer can serve calls of any size on the same stream.
  *   inv_count: 1 / (B_global * K_global) (mean over the full matrix, models/som_layer.py:142).
  */
 int64_t som_loss_scratch_floats(int64_t B, int64_t K);

@@ -327,7 +327,9 @@ weighted_loss_kernel(const float* __restrict__ dist, long long ldd, const long l
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
   const long long nblocks = static_cast<long long>(gridDim.x) * gridDim.y;
-  unsigned int* counter = reinterpret_cast<unsigned int*>(partials + nblocks);
+  // scratch layout: word 0 = completion counter (fixed slot, independent of the grid), partial sums from word 2
+  unsigned int* counter = reinterpret_cast<unsigned int*>(partials);
+  partials += 2;
   if (threadIdx.x == 0) {
     float t = 0.f;
 #pragma unroll
