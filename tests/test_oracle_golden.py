@@ -107,3 +107,19 @@ def test_micro_vector_matches_survey_appendix_b():
     assert abs(float(fx["loss"]) - 1.519182324) < 1e-6
     fx = load_golden("micro_cosine")
     assert abs(float(fx["loss"]) - 0.243644103) < 1e-6
+
+
+@pytest.mark.parametrize("name", FULL)
+def test_torch_port_matches_reference(name):
+    """oracle/som_torch_ref.py (the timed CPU baseline) issues the same ATen calls as the reference: bit-level match."""
+    torch = pytest.importorskip("torch")
+    from oracle import som_torch_ref as R
+    fx = load_golden(name)
+    T = torch.tensor(float(fx["T"]), dtype=torch.float32) if bool(fx["T_is_tensor"]) else float(fx["T"])
+    d, b, loss, gx, gw = R.step(torch.as_tensor(fx["x"]), torch.as_tensor(fx["W"]), torch.as_tensor(fx["grid_positions"]),
+                                T, str(fx["distance_fcn"]), float(fx["g_out"]))
+    np.testing.assert_array_equal(b.numpy(), fx["bmu"])
+    np.testing.assert_allclose(d.numpy(), fx["distances"], rtol=1e-6, atol=1e-7)
+    assert abs(loss.item() - float(fx["loss"])) <= 1e-6 * abs(float(fx["loss"]))
+    assert O.rel_err(gx.numpy(), fx["grad_x"]) < 1e-6
+    assert O.rel_err(gw.numpy(), fx["grad_w"]) < 1e-6

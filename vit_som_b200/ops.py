@@ -13,6 +13,21 @@ from ._lib import SomError, check, ptr, stream_ptr
 
 MODE = {"euclidean": 0, "cosine": 1}
 
+# bench.py sets this to a list to get per-launch CUDA-event timings of the three tensor-core GEMMs
+# (entries: (name, start_event, end_event) recorded on the launching stream).
+GEMM_TIMERS = None
+
+
+def _gemm(name, call):
+    if GEMM_TIMERS is None:
+        return call()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    rc = call()
+    e.record()
+    GEMM_TIMERS.append((name, s, e))
+    return rc
+
 
 def _pad4(n: int) -> int:
     return (n + 3) // 4 * 4
@@ -64,9 +79,9 @@ def fwd_distances(xs: StagedOperand, ws: StagedOperand, want_dist: bool = True, 
         check(L.som_bmu_init(ptr(packed), B, stream_ptr()), "som_bmu_init")
     ldd = _pad4(K)
     dist_buf = torch.empty((B, ldd), device=dev, dtype=torch.float32) if want_dist else None
-    check(L.som_fwd_distances(ptr(xs.hi), ptr(xs.lo), xs.ld, ptr(xs.aux), ptr(ws.hi), ptr(ws.lo), ws.ld, ptr(ws.aux),
-                              B, K, D, xs.mode, idx_offset, ptr(dist_buf), ldd, ptr(packed), stream_ptr()),
-          "som_fwd_distances")
+    check(_gemm("fwd", lambda: L.som_fwd_distances(
+        ptr(xs.hi), ptr(xs.lo), xs.ld, ptr(xs.aux), ptr(ws.hi), ptr(ws.lo), ws.ld, ptr(ws.aux),
+        B, K, D, xs.mode, idx_offset, ptr(dist_buf), ldd, ptr(packed), stream_ptr())), "som_fwd_distances")
     dist = dist_buf[:, :K] if want_dist else None
     return dist, packed
 
@@ -173,13 +188,15 @@ class DistanceFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             xf = _rowmajor(_require_cuda_f32(x.reshape(B, D), "x"))
             dx = torch.empty((B, D), device=dev, dtype=torch.float32)
-            check(L.som_bwd_dx(ptr(r_hi), ptr(r_lo), ldr, ptr(ws.hi), ptr(ws.lo), ws.ld, ptr(xf), xf.stride(0),
-                               ptr(ax), ptr(bx), B, K, D, ptr(dx), D, stream_ptr()), "som_bwd_dx")
+            check(_gemm("dx", lambda: L.som_bwd_dx(ptr(r_hi), ptr(r_lo), ldr, ptr(ws.hi), ptr(ws.lo), ws.ld, ptr(xf),
+                                                   xf.stride(0), ptr(ax), ptr(bx), B, K, D, ptr(dx), D,
+                                                   stream_ptr())), "som_bwd_dx")
             if dx.dtype != x.dtype:
                 dx = dx.to(x.dtype)
         if ctx.needs_input_grad[1]:
             Wf = _rowmajor(_require_cuda_f32(W, "prototypes"))
             dw = torch.empty((K, D), device=dev, dtype=torch.float32)
-            check(L.som_bwd_dw(ptr(r_hi), ptr(r_lo), ldr, ptr(xs.hi), ptr(xs.lo), xs.ld, ptr(Wf), Wf.stride(0),
-                               ptr(aw), ptr(bw), B, K, D, ptr(dw), D, stream_ptr()), "som_bwd_dw")
+            check(_gemm("dw", lambda: L.som_bwd_dw(ptr(r_hi), ptr(r_lo), ldr, ptr(xs.hi), ptr(xs.lo), xs.ld, ptr(Wf),
+                                                   Wf.stride(0), ptr(aw), ptr(bw), B, K, D, ptr(dw), D,
+                                                   stream_ptr())), "som_bwd_dw")
         return dx, dw, None, None, None
