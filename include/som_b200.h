@@ -19,6 +19,9 @@
  *   som_weighted_loss_grad   autograd MeanBackward0/MulBackward0          (autograd of :141-142)
  *   som_bwd_coeffs           EuclideanDistBackward0 / Mm+NormalizeBackward (autograd of :118-122)
  *   som_bwd_dx, som_bwd_dw   the two gradient GEMMs of the same backward
+ *   som_forward              SOMLayer.forward in one call                 models/som_layer.py:83-89
+ *   som_loss_fused           compute_weights + som_loss (+ backward staging) models/som_layer.py:137-152
+ *   som_backward_dw/_dx      backward of the fused loss into prototypes / latents
  *
  * Distance modes: 0 = euclidean (non-squared, ATen `_euclidean_dist` formula
  * sqrt(clamp_min(|x|^2 - 2 x.w + |w|^2, 0))), 1 = cosine (1 - x̂.ŵ with F.normalize eps 1e-12).
@@ -132,6 +135,58 @@ int som_bwd_dw(const float* r_hi, const float* r_lo, int64_t ldr,
                const float* x_hi, const float* x_lo, int64_t ldx,
                const float* w, int64_t ldw, const float* aw, const float* bw,
                int64_t B, int64_t K, int64_t D, float* dw, int64_t lddw, void* stream);
+
+/*
+ * ---- Fused protocol entry points: one call per stage of the reference's call sequence ----------------
+ * (models/vit_som.py:82-86: forward -> update_temperature -> compute_weights -> som_loss, then backward).
+ *
+ * som_forward  = SOMLayer.forward (models/som_layer.py:83-89) in three launches:
+ *   1. operand staging of the latents (and of the prototypes when stage_w != 0: they only change when the
+ *      optimizer steps) + packed[] reset, 2. the tcgen05 distance GEMM with the fused norm / clamp / sqrt /
+ *      argmin epilogue, 3. packed -> int64 BMU (skipped when bmu == NULL: a prototype shard decodes after the
+ *      cross-rank min reduction).
+ *   x [B, ldx], W [K, ldw] raw fp32;  x_hi/x_lo/w_hi/w_lo [rows, ld_stage] staging (ld_stage % 4 == 0, >= D),
+ *   x_aux [B], w_aux [K]; dist [B, ldd] may be NULL (argmin-only inference); K_total = map size for decode.
+ */
+int som_forward(const float* x, int64_t ldx, const float* W, int64_t ldw,
+                int64_t B, int64_t K, int64_t D, int mode, int stage_w, int64_t idx_offset,
+                float* x_hi, float* x_lo, float* x_aux, float* w_hi, float* w_lo, float* w_aux,
+                int64_t ld_stage, float* dist, int64_t ldd, long long* packed, int64_t* bmu,
+                int64_t K_total, void* stream);
+
+/*
+ * som_loss_fused = compute_weights + som_loss (models/som_layer.py:137-152) and, when r_hi != NULL, the
+ * staging of their backward in the same pass over dist[B,K]:
+ *   loss_out   = inv_count * sum_{b,k} w[b,k] dist[b,k]              (w recomputed in registers)
+ *   R_unit     = inv_count * w / dist (0 where dist == 0) | inv_count * w (cosine), tf32 hi/lo split
+ *   row_sum[b] = sum_k R_unit | sum_k R_unit (1 - dist);   col_sum[k] likewise over b
+ * The upstream gradient of the loss is applied later, in the epilogue of the gradient GEMMs.
+ * scratch: at least som_loss_fused_scratch_floats(B, K) floats, word 0 zero on entry (restored on exit).
+ */
+int64_t som_loss_fused_scratch_floats(int64_t B, int64_t K);
+int som_loss_fused(const float* dist, int64_t ldd, const int64_t* bmu, const float* grid_pos,
+                   int64_t B, int64_t K, int64_t k_offset, const float* T_dev, float inv_count, int mode,
+                   float* r_hi, float* r_lo, int64_t ldr, float* row_sum, float* col_sum,
+                   float* scratch, float* loss_out, void* stream);
+
+/*
+ * The two gradient GEMMs of the closed-form backward (ATen _euclidean_dist_backward | MmBackward0 +
+ * normalize backward), with g = *g_dev the upstream gradient of the loss:
+ *   dW[k,:] (+)= g * (c_k W[k,:] - s_k sum_b R_unit[b,k] x~[b,:])     c, s from col_sum / w_aux
+ *   dx[b,:] (+)= g * (c_b x[b,:] - s_b sum_k R_unit[b,k] W~[k,:])     c, s from row_sum / x_aux
+ * euclidean: c = sum, s = 1;  cosine: c = aux^2 * sum, s = aux.  accumulate != 0 adds into the output
+ * (row-chunked batches accumulate dW across chunks).
+ */
+int som_backward_dw(const float* r_hi, const float* r_lo, int64_t ldr,
+                    const float* x_hi, const float* x_lo, int64_t ld_stage,
+                    const float* W, int64_t ldw, const float* col_sum, const float* w_aux,
+                    const float* g_dev, int64_t B, int64_t K, int64_t D, int mode,
+                    float* dW, int64_t lddw, int accumulate, void* stream);
+int som_backward_dx(const float* r_hi, const float* r_lo, int64_t ldr,
+                    const float* w_hi, const float* w_lo, int64_t ld_stage,
+                    const float* x, int64_t ldx, const float* row_sum, const float* x_aux,
+                    const float* g_dev, int64_t B, int64_t K, int64_t D, int mode,
+                    float* dx, int64_t lddx, int accumulate, void* stream);
 
 /*
  * Diagnostic entry point (used by the tests to validate the tensor-core mainloop in isolation):

@@ -186,13 +186,26 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // GROUP threads cooperate on one row (GROUP = 32: warp per row, GROUP = 256: block per row).
+struct PrepSet {
+  const float* src; long long rows; long long ld_src;
+  float* hi; float* lo; float* aux;
+  long long* packed;     // optional: packed[row] = INT64_MAX (argmin identity) for every staged row
+};
+
+// Stages up to two matrices of the same width in one launch (latents and prototypes of one forward).
 template <int GROUP>
 __global__ void __launch_bounds__(256)
-prep_rows_kernel(const float* __restrict__ src, long long rows, int dim, long long ld_src, int mode,
-                 float* __restrict__ hi, float* __restrict__ lo, long long ld_out, float* __restrict__ aux) {
+prep_rows_kernel(const PrepSet sa, const PrepSet sb, long long blocks_a, int dim, int mode, long long ld_out) {
   constexpr int ROWS_PER_BLOCK = 256 / GROUP;
   const int gi = threadIdx.x / GROUP, gt = threadIdx.x % GROUP;
-  const long long row = static_cast<long long>(blockIdx.x) * ROWS_PER_BLOCK + gi;
+  const bool second = static_cast<long long>(blockIdx.x) >= blocks_a;
+  const PrepSet& ps = second ? sb : sa;
+  const float* __restrict__ src = ps.src;
+  float* __restrict__ hi = ps.hi;
+  float* __restrict__ lo = ps.lo;
+  float* __restrict__ aux = ps.aux;
+  const long long rows = ps.rows, ld_src = ps.ld_src;
+  const long long row = (static_cast<long long>(blockIdx.x) - (second ? blocks_a : 0)) * ROWS_PER_BLOCK + gi;
   __shared__ float red[8];
   const bool active = row < rows;
   const float* p = src + (active ? row : 0) * ld_src;
@@ -218,6 +231,7 @@ prep_rows_kernel(const float* __restrict__ src, long long rows, int dim, long lo
     for (int i = 0; i < 8; ++i) ss += red[i];
   }
   if (!active) return;
+  if (ps.packed && gt == 0) ps.packed[row] = 0x7fffffffffffffffLL;
   float denom = 1.f;
   if (mode == 1) {
     denom = fmaxf(sqrtf(ss), 1e-12f);            // F.normalize(p=2, eps=1e-12)
@@ -433,7 +447,130 @@ bwd_coeffs_kernel(const float* __restrict__ G, long long ldg, const float* __res
   }
 }
 
+// Fused forward-loss + backward staging (models/som_layer.py:137-152 and the MeanBackward0 -> MulBackward0 ->
+// distance-backward chain): one pass over dist[B,K] produces
+//   * the loss  inv_count * sum w d  (w recomputed in registers, never stored),
+//   * R_unit = dL/dd / d for unit upstream gradient, as the tf32 hi/lo GEMM operand, and
+//   * its row / column sums (the rank-1 coefficients of the closed-form backward).
+// The upstream gradient g_out multiplies the result in the epilogue of the gradient GEMMs, so backward needs no
+// further pass over B x K.  r_hi == nullptr: loss only (validation / no_grad).
+// thread <-> column k, loop over COEFF_ROWS rows: coalesced reads of dist, coalesced writes of R.
+__global__ void __launch_bounds__(256)
+loss_coeffs_kernel(const float* __restrict__ dist, long long ldd, const long long* __restrict__ bmu,
+                   const float* __restrict__ pos, long long B, long long K, long long k_offset,
+                   const float* __restrict__ T_dev, float inv_count, int mode,
+                   float* __restrict__ r_hi, float* __restrict__ r_lo, long long ldr,
+                   float* __restrict__ row_sum, float* __restrict__ col_sum,
+                   float* __restrict__ partials, float* __restrict__ loss_out) {
+  const long long k = static_cast<long long>(blockIdx.y) * 256 + threadIdx.x;
+  const long long b0 = static_cast<long long>(blockIdx.x) * COEFF_ROWS;
+  const bool col_ok = k < K;
+  const bool want_r = r_hi != nullptr;
+  __shared__ float red[COEFF_ROWS][8];
+  __shared__ float2 pb[COEFF_ROWS];
+  __shared__ float lred[8];
+  __shared__ double dred[256];
+  __shared__ bool is_last;
+  if (threadIdx.x < COEFF_ROWS) {
+    const long long b = b0 + threadIdx.x;
+    float2 p = make_float2(0.f, 0.f);
+    if (b < B) p = __ldg(reinterpret_cast<const float2*>(pos) + bmu[b]);
+    pb[threadIdx.x] = p;
+  }
+  const float T = __ldg(T_dev);
+  const float two_t2 = 2.f * (T * T);
+  const float2 pk = col_ok ? __ldg(reinterpret_cast<const float2*>(pos) + k_offset + k) : make_float2(0.f, 0.f);
+  __syncthreads();
+  float colsum = 0.f, lsum = 0.f;
+#pragma unroll 4
+  for (int r = 0; r < COEFF_ROWS; ++r) {
+    const long long b = b0 + r;
+    float rowterm = 0.f;
+    if (b < B && col_ok) {
+      const float d = __ldg(dist + b * ldd + k);
+      const float w = neighbourhood_weight(pk.x, pk.y, pb[r].x, pb[r].y, two_t2);
+      lsum = fmaf(w, d, lsum);
+      if (want_r) {
+        const float g = inv_count * w;
+        float rv, term;
+        if (mode == 0) {
+          rv = (d == 0.f) ? 0.f : g / d;               // ATen: ratio.masked_fill_(dist == 0, 0)
+          term = rv;
+        } else {
+          rv = g;
+          term = g * (1.f - d);                        // g * (x^ . w^): projection coefficient of normalize backward
+        }
+        const float h = tf32_rna(rv);
+        r_hi[b * ldr + k] = h;
+        r_lo[b * ldr + k] = tf32_rna(rv - h);
+        colsum += term;
+        rowterm = term;
+      }
+    }
+    if (want_r) {
+      rowterm = warp_sum(rowterm);
+      if ((threadIdx.x & 31) == 0) red[r][threadIdx.x >> 5] = rowterm;
+    }
+  }
+  lsum = warp_sum(lsum);
+  if ((threadIdx.x & 31) == 0) lred[threadIdx.x >> 5] = lsum;
+  __syncthreads();
+  if (want_r) {
+    if (threadIdx.x < COEFF_ROWS) {
+      const long long b = b0 + threadIdx.x;
+      if (b < B) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[threadIdx.x][i];
+        atomicAdd(row_sum + b, t);
+      }
+    }
+    if (col_ok) atomicAdd(col_sum + k, colsum);
+  }
+  // deterministic loss: per-block partial, last block reduces all partials in a fixed order in fp64
+  const long long nblocks = static_cast<long long>(gridDim.x) * gridDim.y;
+  unsigned int* counter = reinterpret_cast<unsigned int*>(partials);
+  partials += 2;
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += lred[i];
+    partials[static_cast<long long>(blockIdx.y) * gridDim.x + blockIdx.x] = t;
+    __threadfence();
+    const unsigned int done = atomicAdd(counter, 1u);
+    is_last = (done == nblocks - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double acc = 0.0;
+  for (long long i = threadIdx.x; i < nblocks; i += 256) acc += static_cast<double>(__ldcg(partials + i));
+  dred[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) dred[threadIdx.x] += dred[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    *loss_out = static_cast<float>(dred[0] * static_cast<double>(inv_count));
+    *counter = 0u;                                   // restore the zero state for the next call
+  }
+}
+
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+int launch_prep(const PrepSet& a, const PrepSet& b, int64_t dim, int mode, int64_t ld_out, cudaStream_t st) {
+  const int per_block = dim <= 1024 ? 8 : 1;
+  const long long blocks_a = (a.rows + per_block - 1) / per_block;
+  const long long blocks_b = b.src ? (b.rows + per_block - 1) / per_block : 0;
+  if (blocks_a + blocks_b > 0x7fffffffLL) return fail(SOM_ERR_ARG, "too many rows to stage in one launch");
+  const unsigned grid = static_cast<unsigned>(blocks_a + blocks_b);
+  if (dim <= 1024) prep_rows_kernel<32><<<grid, 256, 0, st>>>(a, b, blocks_a, static_cast<int>(dim), mode, ld_out);
+  else             prep_rows_kernel<256><<<grid, 256, 0, st>>>(a, b, blocks_a, static_cast<int>(dim), mode, ld_out);
+  SOM_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return SOM_OK;
+}
 
 }  // namespace
 
@@ -442,7 +579,7 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 // ------------------------------------------------------------------------------------------------
 extern "C" {
 
-int som_b200_abi_version(void) { return 1; }
+int som_b200_abi_version(void) { return 2; }
 const char* som_last_error(void) { return g_last_error.c_str(); }
 int64_t som_launch_count(void) { return g_launches.load(); }
 void som_launch_count_reset(void) { g_launches.store(0); }
@@ -461,16 +598,8 @@ int som_prep_rows(const float* src, int64_t rows, int64_t dim, int64_t ld_src, i
   if ((ld_out & 3) != 0 || ((reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 15) != 0)
     return fail(SOM_ERR_ARG, "som_prep_rows: hi/lo must be 16-byte aligned with ld_out % 4 == 0");
   if (mode != SOM_MODE_EUCLIDEAN && mode != SOM_MODE_COSINE) return fail(SOM_ERR_ARG, "som_prep_rows: bad mode");
-  if (dim <= 1024) {
-    prep_rows_kernel<32><<<static_cast<unsigned>((rows + 7) / 8), 256, 0, as_stream(stream)>>>(
-        src, rows, static_cast<int>(dim), ld_src, mode, hi, lo, ld_out, aux);
-  } else {
-    prep_rows_kernel<256><<<static_cast<unsigned>(rows), 256, 0, as_stream(stream)>>>(
-        src, rows, static_cast<int>(dim), ld_src, mode, hi, lo, ld_out, aux);
-  }
-  SOM_CUDA(cudaGetLastError());
-  g_launches.fetch_add(1);
-  return SOM_OK;
+  PrepSet a{src, rows, ld_src, hi, lo, aux, nullptr}, none{};
+  return launch_prep(a, none, dim, mode, ld_out, as_stream(stream));
 }
 
 int som_bmu_init(long long* packed, int64_t B, void* stream) {
@@ -591,6 +720,81 @@ int som_bwd_dw(const float* r_hi, const float* r_lo, int64_t ldr, const float* x
   e.alpha = aw; e.beta = bw; e.src = w; e.lds = ldw; e.out = dw; e.ldo = lddw;
   // C[K,D] = R^T[K,B] . x[B,D]: A = R read MN-major (K contiguous), B = x MN-major (D contiguous)
   return launch_gemm(som::EPI_GRAD, r_hi, r_lo, ldr, 1, x_hi, x_lo, ldx, 1, K, D, B, 0, 0, 3, e, as_stream(stream));
+}
+
+// ---- fused protocol entry points (one call per stage of the reference's call sequence) ----------------------
+
+int som_forward(const float* x, int64_t ldx, const float* W, int64_t ldw, int64_t B, int64_t K, int64_t D, int mode,
+                int stage_w, int64_t idx_offset, float* x_hi, float* x_lo, float* x_aux, float* w_hi, float* w_lo,
+                float* w_aux, int64_t ld_stage, float* dist, int64_t ldd, long long* packed, int64_t* bmu,
+                int64_t K_total, void* stream) {
+  DeviceInfo di;
+  if (int rc = device_info(di)) return rc;
+  if (!x || !x_hi || !x_lo || !x_aux || !w_hi || !w_lo || !w_aux || !packed)
+    return fail(SOM_ERR_ARG, "som_forward: null pointer");
+  if (stage_w && !W) return fail(SOM_ERR_ARG, "som_forward: prototypes required when stage_w is set");
+  if (B <= 0 || K <= 0 || D <= 0 || D > (1ll << 30) || ldx < D || (stage_w && ldw < D) || ld_stage < D)
+    return fail(SOM_ERR_ARG, "som_forward: bad shape");
+  if ((ld_stage & 3) != 0) return fail(SOM_ERR_ARG, "som_forward: ld_stage must be a multiple of 4");
+  if (mode != SOM_MODE_EUCLIDEAN && mode != SOM_MODE_COSINE) return fail(SOM_ERR_ARG, "som_forward: bad mode");
+  PrepSet a{x, B, ldx, x_hi, x_lo, x_aux, packed}, b{};
+  if (stage_w) b = PrepSet{W, K, ldw, w_hi, w_lo, w_aux, nullptr};
+  if (int rc = launch_prep(a, b, D, mode, ld_stage, as_stream(stream))) return rc;
+  if (int rc = som_fwd_distances(x_hi, x_lo, ld_stage, x_aux, w_hi, w_lo, ld_stage, w_aux, B, K, D, mode, idx_offset,
+                                 dist, ldd, packed, stream))
+    return rc;
+  if (bmu) return som_bmu_decode(packed, B, K_total > 0 ? K_total : K, bmu, nullptr, stream);
+  return SOM_OK;
+}
+
+int som_loss_fused(const float* dist, int64_t ldd, const int64_t* bmu, const float* grid_pos, int64_t B, int64_t K,
+                   int64_t k_offset, const float* T_dev, float inv_count, int mode, float* r_hi, float* r_lo,
+                   int64_t ldr, float* row_sum, float* col_sum, float* scratch, float* loss_out, void* stream) {
+  DeviceInfo di;
+  if (int rc = device_info(di)) return rc;
+  if (!dist || !bmu || !grid_pos || !T_dev || !scratch || !loss_out || B <= 0 || K <= 0 || ldd < K)
+    return fail(SOM_ERR_ARG, "som_loss_fused: bad argument");
+  if (mode != SOM_MODE_EUCLIDEAN && mode != SOM_MODE_COSINE) return fail(SOM_ERR_ARG, "som_loss_fused: bad mode");
+  if (r_hi) {
+    if (!r_lo || !row_sum || !col_sum || ldr < K) return fail(SOM_ERR_ARG, "som_loss_fused: bad backward staging");
+    SOM_CUDA(cudaMemsetAsync(row_sum, 0, sizeof(float) * B, as_stream(stream)));
+    SOM_CUDA(cudaMemsetAsync(col_sum, 0, sizeof(float) * K, as_stream(stream)));
+  }
+  dim3 grid(static_cast<unsigned>((B + COEFF_ROWS - 1) / COEFF_ROWS), static_cast<unsigned>((K + 255) / 256));
+  loss_coeffs_kernel<<<grid, 256, 0, as_stream(stream)>>>(dist, ldd, reinterpret_cast<const long long*>(bmu), grid_pos,
+                                                         B, K, k_offset, T_dev, inv_count, mode, r_hi, r_lo, ldr,
+                                                         row_sum, col_sum, scratch, loss_out);
+  SOM_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return SOM_OK;
+}
+
+int64_t som_loss_fused_scratch_floats(int64_t B, int64_t K) {
+  return ((B + COEFF_ROWS - 1) / COEFF_ROWS) * ((K + 255) / 256) + 2;
+}
+
+int som_backward_dw(const float* r_hi, const float* r_lo, int64_t ldr, const float* x_hi, const float* x_lo,
+                    int64_t ld_stage, const float* W, int64_t ldw, const float* col_sum, const float* w_aux,
+                    const float* g_dev, int64_t B, int64_t K, int64_t D, int mode, float* dW, int64_t lddw,
+                    int accumulate, void* stream) {
+  if (!W || !col_sum || !g_dev || !dW || ldw < D || lddw < D) return fail(SOM_ERR_ARG, "som_backward_dw: bad argument");
+  if (mode == SOM_MODE_COSINE && !w_aux) return fail(SOM_ERR_ARG, "som_backward_dw: cosine needs the reciprocal norms");
+  som::EpiParams e{};
+  e.sum = col_sum; e.aux = w_aux; e.g_dev = g_dev; e.mode = mode; e.accumulate = accumulate;
+  e.src = W; e.lds = ldw; e.out = dW; e.ldo = lddw;
+  return launch_gemm(som::EPI_GRAD, r_hi, r_lo, ldr, 1, x_hi, x_lo, ld_stage, 1, K, D, B, 0, 0, 3, e, as_stream(stream));
+}
+
+int som_backward_dx(const float* r_hi, const float* r_lo, int64_t ldr, const float* w_hi, const float* w_lo,
+                    int64_t ld_stage, const float* x, int64_t ldx, const float* row_sum, const float* x_aux,
+                    const float* g_dev, int64_t B, int64_t K, int64_t D, int mode, float* dx, int64_t lddx,
+                    int accumulate, void* stream) {
+  if (!x || !row_sum || !g_dev || !dx || ldx < D || lddx < D) return fail(SOM_ERR_ARG, "som_backward_dx: bad argument");
+  if (mode == SOM_MODE_COSINE && !x_aux) return fail(SOM_ERR_ARG, "som_backward_dx: cosine needs the reciprocal norms");
+  som::EpiParams e{};
+  e.sum = row_sum; e.aux = x_aux; e.g_dev = g_dev; e.mode = mode; e.accumulate = accumulate;
+  e.src = x; e.lds = ldx; e.out = dx; e.ldo = lddx;
+  return launch_gemm(som::EPI_GRAD, r_hi, r_lo, ldr, 0, w_hi, w_lo, ld_stage, 1, B, D, K, 0, 0, 3, e, as_stream(stream));
 }
 
 int som_debug_gemm(const float* a_hi, const float* a_lo, int64_t lda, int a_mn, const float* b_hi, const float* b_lo,

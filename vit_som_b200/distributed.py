@@ -1,0 +1,188 @@
+"""Multi-GPU execution of the SOM hot path: one process per GPU, ``torch.distributed`` (NCCL over NVLink 5 /
+NVSwitch) for the exchange steps.  The reference has no distributed code of its own; what it gets implicitly is
+Lightning's DDP (``experiments/benchmarking/train_vit_som.py:45,86-87``), i.e. a batch-sharded data-parallel
+step with an all-reduce of every gradient including ``som_layer.prototypes``.
+
+Two partitionings:
+
+* :class:`DataParallelSOM` - batch rows sharded, prototypes replicated.  The only exchange is the prototype
+  gradient ``dW[K, D]`` (mean over ranks, DDP semantics).  The all-reduce is issued on a side stream as soon as the
+  dW GEMM is enqueued, so it runs under the dx GEMM (and, in a full model, under the ViT backward).
+* :class:`PrototypeShardedSOM` - prototypes sharded in contiguous row blocks of the map (rank r owns map cells
+  ``[r*K/G, (r+1)*K/G)``), latents replicated.  Exchanges per step: (1) the per-row packed ``(key, global index)``
+  minima, ``all_reduce(MIN)`` on int64 - B * 8 bytes; NCCL has no MINLOC, the packing gives the first-index
+  tie-break of ``torch.argmin``; (2) the scalar loss, ``all_reduce(SUM)``; (3) ``dx[B, D]``, ``all_reduce(SUM)``
+  of the per-shard partial gradients.  ``dW`` of the local shard needs no exchange.
+
+The helpers at the top are device-agnostic (they run on CPU tensors over gloo in the unit tests); the numeric
+work stays in libsom_b200.so.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from ._lib import SomError
+from .som_layer import NeighbourhoodWeights, SOMLayer
+
+INT64_MAX = 0x7FFFFFFFFFFFFFFF
+
+
+# ------------------------------------------------------------------------------------------------------------
+# exchange helpers (device-agnostic)
+# ------------------------------------------------------------------------------------------------------------
+def shard_range(n_items: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous block [begin, end) of ``n_items`` owned by ``rank``; the first ``n_items % world`` ranks get one
+    extra item, so any map size shards over any world size."""
+    if world <= 0 or not 0 <= rank < world:
+        raise ValueError("bad rank / world size")
+    base, extra = divmod(n_items, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def reduce_packed_min(packed: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place elementwise signed-int64 MIN over ranks of the packed (ordered key << 32 | global index) minima.
+    The smaller key wins; on equal keys the smaller global index wins (= torch.argmin over the full map)."""
+    if packed.dtype != torch.int64:
+        raise TypeError("packed minima must be int64")
+    dist.all_reduce(packed, op=dist.ReduceOp.MIN, group=group)
+    return packed
+
+
+def unpack_bmu(packed: torch.Tensor, k_total: int) -> torch.Tensor:
+    """Global BMU index = low 32 bits of the packed minimum (rows that never saw a finite key fall back to 0,
+    like som_bmu_decode)."""
+    idx = packed & 0xFFFFFFFF
+    return torch.where(idx < k_total, idx, torch.zeros_like(idx))
+
+
+def all_reduce_sum(t: torch.Tensor, group=None) -> torch.Tensor:
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def all_reduce_mean(t: torch.Tensor, group=None) -> torch.Tensor:
+    """DDP semantics for a replicated parameter's gradient: sum over ranks / world size."""
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    t.div_(dist.get_world_size(group))
+    return t
+
+
+# ------------------------------------------------------------------------------------------------------------
+# batch-sharded data parallel
+# ------------------------------------------------------------------------------------------------------------
+class DataParallelSOM:
+    """Attach DDP-equivalent gradient averaging to a :class:`SOMLayer` whose batch is sharded over ranks.
+
+    ``DataParallelSOM(layer)`` broadcasts the prototypes from rank 0 and installs the layer's dW hook: inside the
+    backward, right after the dW GEMM has been enqueued, the all-reduce (+ 1/world scaling) of dW is issued on a
+    communication stream; the dx GEMM then runs concurrently, and the compute stream joins the communication stream
+    before backward returns dW to autograd.  The local loss is the mean over the local rows, as under DDP."""
+
+    def __init__(self, layer: SOMLayer, group=None, broadcast: bool = True):
+        if not dist.is_initialized():
+            raise SomError("DataParallelSOM needs an initialised torch.distributed process group")
+        self.layer, self.group = layer, group
+        self.world = dist.get_world_size(group)
+        dev = layer.prototypes.device
+        self.comm_stream = torch.cuda.Stream(dev) if dev.type == "cuda" else None
+        if broadcast:
+            with torch.no_grad():
+                dist.broadcast(layer.prototypes.data, src=dist.get_global_rank(group, 0) if group is not None else 0,
+                               group=group)
+        layer._dw_hook = self._on_dw
+
+    def _on_dw(self, dw: torch.Tensor):
+        """Called from FusedLossFn.backward with the freshly enqueued dW; returns the join callable."""
+        if self.comm_stream is None:                       # CPU tensors (gloo unit tests)
+            all_reduce_mean(dw, self.group)
+            return None
+        cur = torch.cuda.current_stream(dw.device)
+        self.comm_stream.wait_stream(cur)
+        with torch.cuda.stream(self.comm_stream):
+            all_reduce_mean(dw, self.group)
+        dw.record_stream(self.comm_stream)
+        return lambda: cur.wait_stream(self.comm_stream)
+
+    def detach(self):
+        self.layer._dw_hook = None
+
+
+# ------------------------------------------------------------------------------------------------------------
+# prototype-sharded
+# ------------------------------------------------------------------------------------------------------------
+class _ShardedLossFn(torch.autograd.Function):
+    """Global loss of a prototype-sharded map as one autograd node over (x, W_shard): local fused loss kernel,
+    scalar all-reduce; backward = local gradient GEMMs + all-reduce of the partial dx."""
+
+    @staticmethod
+    def forward(ctx, x, W, state, bmu, grid_pos, T_dev, inv_count, k_offset, want_grad, group):
+        loss = ops.FusedLossFn.forward(ctx, x, W, state, bmu, grid_pos, T_dev, inv_count, k_offset, want_grad, None)
+        ctx.group = group
+        return all_reduce_sum(loss, group)
+
+    @staticmethod
+    def backward(ctx, g_out):
+        grads = ops.FusedLossFn.backward(ctx, g_out)
+        dx = grads[0]
+        if dx is not None:
+            all_reduce_sum(dx, ctx.group)
+        return grads + (None,) * (10 - len(grads))
+
+
+class PrototypeShardedSOM(SOMLayer):
+    """A SOM whose prototypes are sharded over the ranks of ``group`` (large maps, BASELINE config 5).
+
+    Same constructor dict and call protocol as :class:`SOMLayer`; ``prototypes`` holds only the local block
+    ``[k_begin, k_end)`` of the map (drawn from the same RNG stream as the full map so that a seeded construction
+    matches the unsharded layer), ``grid_positions`` holds the full grid.  ``forward`` returns the *local* slice
+    of the distance matrix ``[B, K_local]`` and the *global* BMU indices; ``som_loss`` returns the global loss."""
+
+    def __init__(self, config, group=None):
+        if not dist.is_initialized():
+            raise SomError("PrototypeShardedSOM needs an initialised torch.distributed process group")
+        super().__init__(config)
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.k_total = self.n_prototypes
+        self.k_begin, self.k_end = shard_range(self.k_total, self.world, self.rank)
+        if self.k_end <= self.k_begin:
+            raise ValueError(f"map of {self.k_total} cells cannot be sharded over {self.world} ranks")
+        full = self.prototypes.data
+        self.prototypes = torch.nn.Parameter(full[self.k_begin:self.k_end].clone())
+
+    def _forward_impl(self, x, want_dist=True):
+        if x.dim() > 2:
+            x = x.flatten(start_dim=1)
+        if not x.is_cuda or not self.prototypes.is_cuda:
+            raise SomError("PrototypeShardedSOM runs on B200s only: move the module and its input to cuda")
+        if x.dim() != 2 or x.shape[1] != self.latent_dim:
+            raise ValueError(f"latent shape {tuple(x.shape)} does not end in latent_dim {self.latent_dim}")
+        mode = self._mode()
+        ws, refill = self._staged_prototypes(mode)
+        try:
+            state, _ = ops.forward(x, self.prototypes, mode, ws, refill, want_dist=want_dist, want_bmu=False,
+                                   idx_offset=self.k_begin, k_total=self.k_total)
+        except Exception:
+            self._w_cache = None
+            raise
+        reduce_packed_min(state.packed, self.group)          # exchange step 1: B x 8 bytes over NVLink
+        bmu = ops.bmu_decode(state.packed, self.k_total)
+        if not want_dist:
+            return None, bmu
+        state.x_in, state.W_in = x, self.prototypes
+        dist_local = ops.DistanceFn.apply(x, self.prototypes, state)
+        dist_local._som_state = state
+        return dist_local, bmu
+
+    def som_loss(self, weights, distances):
+        state = getattr(distances, "_som_state", None)
+        if not (isinstance(weights, NeighbourhoodWeights) and weights._dense is None and state is not None):
+            raise SomError("PrototypeShardedSOM.som_loss needs the lazy weights of compute_weights() and the "
+                           "distances returned by this layer's forward")
+        B = distances.shape[0]
+        want_grad = torch.is_grad_enabled() and (state.x_in.requires_grad or state.W_in.requires_grad)
+        return _ShardedLossFn.apply(state.x_in, state.W_in, state, weights.bmu, self.grid_positions, weights.T_dev,
+                                    1.0 / (B * self.k_total), self.k_begin, want_grad, self.group)

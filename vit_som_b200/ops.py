@@ -1,8 +1,16 @@
-"""Tensor-level wrappers over the C-ABI (include/som_b200.h) and the two autograd functions.
+"""Tensor-level wrappers over the C-ABI (include/som_b200.h) and the autograd functions of the SOM layer.
 
 PyTorch is plumbing here: it owns device memory (caching allocator), the current stream and the
 autograd graph.  All arithmetic of the hot path happens in ``libsom_b200.so``; nothing in this file
 computes distances, weights, losses or gradients with torch ops, and CPU tensors are rejected.
+
+Launches per training step (reference call sequence models/vit_som.py:82-86 + backward):
+
+    forward   som_forward      staging kernel (x and, when stale, W) -> tcgen05 GEMM + distance/argmin epilogue
+                               -> BMU decode                                                       3 launches
+    loss      som_loss_fused   loss + backward staging (R hi/lo, row/column sums) in one pass       1 launch
+    backward  som_backward_dw  tcgen05 GEMM  R^T x~  with the gradient epilogue                     1 launch
+              som_backward_dx  tcgen05 GEMM  R W~    with the gradient epilogue                     1 launch
 """
 from __future__ import annotations
 
@@ -43,47 +51,100 @@ def _require_cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
     return t
 
 
-class StagedOperand:
-    """tf32 hi/lo split of a row-major matrix plus its per-row aux vector (|row|^2 or 1/max(|row|,eps))."""
-    __slots__ = ("hi", "lo", "aux", "rows", "dim", "ld", "mode")
+def _rowmajor(t: torch.Tensor) -> torch.Tensor:
+    """A 2-D view with unit inner stride and non-overlapping rows (what the kernels index with an ld)."""
+    if t.stride(1) != 1 or t.stride(0) < t.shape[1]:
+        t = t.contiguous()
+    return t
 
-    def __init__(self, src: torch.Tensor, mode: int):
-        src = _require_cuda_f32(src, "operand")
-        if src.dim() != 2:
-            raise ValueError("operand must be 2-D")
-        if src.stride(1) != 1:
-            src = src.contiguous()
-        rows, dim = src.shape
-        if rows == 0 or dim == 0:
+
+class Staging:
+    """tf32 hi/lo split of a row-major [rows, dim] matrix plus its per-row aux vector (|row|^2 for euclidean,
+    1/max(|row|, eps) for cosine), carved out of one flat allocation: hi | lo | aux."""
+    __slots__ = ("buf", "rows", "dim", "ld", "mode", "hi", "lo", "aux", "key")
+
+    def __init__(self, rows: int, dim: int, mode: int, device):
+        if rows <= 0 or dim <= 0:
             raise ValueError("empty operand")
-        ld = _pad4(dim)
-        self.hi = torch.empty((rows, ld), device=src.device, dtype=torch.float32)
-        self.lo = torch.empty((rows, ld), device=src.device, dtype=torch.float32)
-        self.aux = torch.empty((rows,), device=src.device, dtype=torch.float32)
-        self.rows, self.dim, self.ld, self.mode = rows, dim, ld, mode
-        L = _lib.lib()
-        check(L.som_prep_rows(ptr(src), rows, dim, src.stride(0), mode, ptr(self.hi), ptr(self.lo), ld,
-                              ptr(self.aux), stream_ptr()), "som_prep_rows")
+        self.rows, self.dim, self.mode = rows, dim, mode
+        self.ld = _pad4(dim)
+        n = rows * self.ld
+        self.buf = torch.empty((2 * n + rows,), device=device, dtype=torch.float32)
+        base = self.buf.data_ptr()
+        self.hi, self.lo, self.aux = base, base + 4 * n, base + 8 * n
+        self.key = None                       # identity of the tensor version staged here (prototype cache)
+
+    def aux_tensor(self) -> torch.Tensor:
+        n = self.rows * self.ld
+        return self.buf[2 * n:]
 
 
-def fwd_distances(xs: StagedOperand, ws: StagedOperand, want_dist: bool = True, idx_offset: int = 0,
-                  packed: torch.Tensor | None = None):
-    """Distances [B, K] (view of a [B, pad4(K)] buffer) and the packed (key, index) minima [B]."""
-    if xs.dim != ws.dim or xs.mode != ws.mode:
-        raise ValueError("latent and prototype staging do not match")
-    B, K, D = xs.rows, ws.rows, xs.dim
-    dev = xs.hi.device
-    L = _lib.lib()
-    if packed is None:
-        packed = torch.empty((B,), device=dev, dtype=torch.int64)
-        check(L.som_bmu_init(ptr(packed), B, stream_ptr()), "som_bmu_init")
+def stage_rows(src: torch.Tensor, mode: int) -> Staging:
+    """Stand-alone staging of one matrix (som_prep_rows)."""
+    src = _rowmajor(_require_cuda_f32(src, "operand"))
+    if src.dim() != 2:
+        raise ValueError("operand must be 2-D")
+    st = Staging(src.shape[0], src.shape[1], mode, src.device)
+    check(_lib.lib().som_prep_rows(ptr(src), st.rows, st.dim, src.stride(0), mode, st.hi, st.lo, st.ld, st.aux,
+                                   stream_ptr()), "som_prep_rows")
+    return st
+
+
+class ForwardState:
+    """What one forward leaves behind for the loss and the backward: raw and staged operands and the distances."""
+    __slots__ = ("x", "W", "xs", "ws", "mode", "B", "K", "D", "dist_buf", "ldd", "packed", "idx_offset",
+                 "x_in", "W_in")
+
+
+def forward(x: torch.Tensor, W: torch.Tensor, mode: int, ws: Staging | None = None, stage_w: bool = True,
+            want_dist: bool = True, want_bmu: bool = True, idx_offset: int = 0, k_total: int | None = None):
+    """SOMLayer.forward through ``som_forward``.  Returns (state, bmu or None).
+
+    ``ws`` is a prototype staging owned by the caller (the layer caches it across steps); it is (re)filled when
+    ``stage_w`` is true."""
+    xf = _rowmajor(_require_cuda_f32(x, "x"))
+    Wf = _rowmajor(_require_cuda_f32(W, "prototypes"))
+    if xf.dim() != 2 or Wf.dim() != 2 or xf.shape[1] != Wf.shape[1]:
+        raise ValueError("latents [B, D] and prototypes [K, D] do not match")
+    B, D = xf.shape
+    K = Wf.shape[0]
+    if B == 0:
+        raise ValueError("empty batch")
+    dev = xf.device
+    xs = Staging(B, D, mode, dev)
+    if ws is None:
+        ws, stage_w = Staging(K, D, mode, dev), True
+    elif ws.rows != K or ws.dim != D or ws.mode != mode:
+        raise ValueError("prototype staging does not match the prototypes")
     ldd = _pad4(K)
     dist_buf = torch.empty((B, ldd), device=dev, dtype=torch.float32) if want_dist else None
-    check(_gemm("fwd", lambda: L.som_fwd_distances(
-        ptr(xs.hi), ptr(xs.lo), xs.ld, ptr(xs.aux), ptr(ws.hi), ptr(ws.lo), ws.ld, ptr(ws.aux),
-        B, K, D, xs.mode, idx_offset, ptr(dist_buf), ldd, ptr(packed), stream_ptr())), "som_fwd_distances")
-    dist = dist_buf[:, :K] if want_dist else None
-    return dist, packed
+    packed = torch.empty((B,), device=dev, dtype=torch.int64)
+    bmu = torch.empty((B,), device=dev, dtype=torch.int64) if want_bmu else None
+    L = _lib.lib()
+    if GEMM_TIMERS is None:
+        check(L.som_forward(
+            ptr(xf), xf.stride(0), ptr(Wf), Wf.stride(0), B, K, D, mode, 1 if stage_w else 0, idx_offset,
+            xs.hi, xs.lo, xs.aux, ws.hi, ws.lo, ws.aux, xs.ld, ptr(dist_buf), ldd, ptr(packed), ptr(bmu),
+            k_total if k_total is not None else K, stream_ptr()), "som_forward")
+    else:
+        # instrumented run (bench.py roofline leg): the same launches issued one by one so that the CUDA events
+        # bracket the tensor-core kernel alone
+        check(L.som_prep_rows(ptr(xf), B, D, xf.stride(0), mode, xs.hi, xs.lo, xs.ld, xs.aux, stream_ptr()),
+              "som_prep_rows")
+        if stage_w:
+            check(L.som_prep_rows(ptr(Wf), K, D, Wf.stride(0), mode, ws.hi, ws.lo, ws.ld, ws.aux, stream_ptr()),
+                  "som_prep_rows")
+        check(L.som_bmu_init(ptr(packed), B, stream_ptr()), "som_bmu_init")
+        check(_gemm("fwd", lambda: L.som_fwd_distances(xs.hi, xs.lo, xs.ld, xs.aux, ws.hi, ws.lo, ws.ld, ws.aux,
+                                                       B, K, D, mode, idx_offset, ptr(dist_buf), ldd, ptr(packed),
+                                                       stream_ptr())), "som_fwd_distances")
+        if bmu is not None:
+            check(L.som_bmu_decode(ptr(packed), B, k_total if k_total is not None else K, ptr(bmu), None,
+                                   stream_ptr()), "som_bmu_decode")
+    st = ForwardState()
+    st.x, st.W, st.xs, st.ws, st.mode = xf, Wf, xs, ws, mode
+    st.B, st.K, st.D, st.dist_buf, st.ldd, st.packed, st.idx_offset = B, K, D, dist_buf, ldd, packed, idx_offset
+    return st, bmu
 
 
 def bmu_decode(packed: torch.Tensor, k_total: int, want_min: bool = False):
@@ -106,8 +167,7 @@ def neighbourhood(bmu: torch.Tensor, grid_pos: torch.Tensor, T_dev: torch.Tensor
 _scratch = {}
 
 
-def _loss_scratch(device, B: int, K: int) -> torch.Tensor:
-    n = int(_lib.lib().som_loss_scratch_floats(B, K))
+def _loss_scratch(device, n: int) -> torch.Tensor:
     key = (device, torch.cuda.current_stream(device).cuda_stream)
     buf = _scratch.get(key)
     if buf is None or buf.numel() < n:
@@ -116,24 +176,89 @@ def _loss_scratch(device, B: int, K: int) -> torch.Tensor:
     return buf
 
 
-def _rowmajor(t: torch.Tensor) -> torch.Tensor:
-    """A 2-D view with unit inner stride and non-overlapping rows (what the kernels index with an ld)."""
-    if t.stride(1) != 1 or t.stride(0) < t.shape[1]:
-        t = t.contiguous()
-    return t
+def _grad_scalar(g_out: torch.Tensor) -> torch.Tensor:
+    g = g_out.reshape(1)
+    if g.dtype != torch.float32:
+        g = g.float()
+    return g.contiguous()
+
+
+class FusedLossFn(torch.autograd.Function):
+    """loss = inv_count * sum_k w(bmu, T)[b,k] * dist(x, W)[b,k] as ONE autograd node over (x, W).
+
+    Forward is one kernel over the distances the layer's forward already produced (``state``): it emits the loss
+    and, when a gradient will be needed, the staged backward operand R and its row/column sums.  Backward is the
+    two tcgen05 gradient GEMMs; the upstream gradient enters through their epilogue.  The B x K weight matrix and
+    the B x K upstream-gradient matrix of the reference's autograd graph are never formed.
+    (models/som_layer.py:137-152 + MeanBackward0 -> MulBackward0 -> EuclideanDistBackward0 | MmBackward0)"""
+
+    @staticmethod
+    def forward(ctx, x, W, state, bmu, grid_pos, T_dev, inv_count, k_offset, want_grad, dw_hook):
+        B, K = state.B, state.K
+        dev = state.dist_buf.device
+        L = _lib.lib()
+        loss = torch.empty((), device=dev, dtype=torch.float32)
+        scratch = _loss_scratch(dev, int(L.som_loss_fused_scratch_floats(B, K)))
+        ldr = _pad4(K)
+        if want_grad:
+            rbuf = torch.empty((2 * B * ldr + B + K,), device=dev, dtype=torch.float32)
+            base = rbuf.data_ptr()
+            r_hi, r_lo = base, base + 4 * B * ldr
+            row_sum, col_sum = base + 8 * B * ldr, base + 8 * B * ldr + 4 * B
+        else:
+            rbuf, r_hi, r_lo, row_sum, col_sum = None, None, None, None, None
+        check(L.som_loss_fused(ptr(state.dist_buf), state.ldd, ptr(bmu), ptr(grid_pos), B, K, k_offset, ptr(T_dev),
+                               inv_count, state.mode, r_hi, r_lo, ldr, row_sum, col_sum, ptr(scratch), ptr(loss),
+                               stream_ptr()), "som_loss_fused")
+        ctx.state, ctx.rbuf, ctx.ptrs, ctx.ldr = state, rbuf, (r_hi, r_lo, row_sum, col_sum), ldr
+        ctx.x_dtype, ctx.x_shape, ctx.dw_hook = x.dtype, x.shape, dw_hook
+        ctx.save_for_backward(bmu, grid_pos, T_dev)     # keeps them alive; the kernels no longer need them
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_out):
+        st = ctx.state
+        if ctx.rbuf is None:
+            raise SomError("som_loss was evaluated without gradient staging (no_grad) but backward was requested")
+        r_hi, r_lo, row_sum, col_sum = ctx.ptrs
+        B, K, D, mode = st.B, st.K, st.D, st.mode
+        dev = st.dist_buf.device
+        L = _lib.lib()
+        g = _grad_scalar(g_out)
+        dx = dw = join = None
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty((K, D), device=dev, dtype=torch.float32)
+            check(_gemm("dw", lambda: L.som_backward_dw(r_hi, r_lo, ctx.ldr, st.xs.hi, st.xs.lo, st.xs.ld, ptr(st.W),
+                                                        st.W.stride(0), col_sum, st.ws.aux, ptr(g), B, K, D, mode,
+                                                        ptr(dw), D, 0, stream_ptr())), "som_backward_dw")
+            if ctx.dw_hook is not None:
+                join = ctx.dw_hook(dw)          # data-parallel: start the prototype-gradient all-reduce now
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((B, D), device=dev, dtype=torch.float32)
+            check(_gemm("dx", lambda: L.som_backward_dx(r_hi, r_lo, ctx.ldr, st.ws.hi, st.ws.lo, st.ws.ld, ptr(st.x),
+                                                        st.x.stride(0), row_sum, st.xs.aux, ptr(g), B, K, D, mode,
+                                                        ptr(dx), D, 0, stream_ptr())), "som_backward_dx")
+            if dx.dtype != ctx.x_dtype:
+                dx = dx.to(ctx.x_dtype)
+            dx = dx.view(ctx.x_shape)
+        if join is not None:
+            join()                              # compute stream waits for the communication stream
+        return dx, dw, None, None, None, None, None, None, None, None
 
 
 class WeightedLossFn(torch.autograd.Function):
-    """loss = inv_count * sum(w(bmu, T) * dist)  — models/som_layer.py:137-152 fused; w is never stored."""
+    """loss = inv_count * sum(w(bmu, T) * dist) for a caller-supplied dense ``dist`` (general path: the distances
+    did not come from this layer's forward, or were modified).  models/som_layer.py:137-152; w is never stored."""
 
     @staticmethod
     def forward(ctx, dist, bmu, grid_pos, T_dev, inv_count, k_offset):
         dist_c = _rowmajor(_require_cuda_f32(dist, "distances"))
         B, K = dist_c.shape
         loss = torch.empty((), device=dist_c.device, dtype=torch.float32)
-        scratch = _loss_scratch(dist_c.device, B, K)
-        check(_lib.lib().som_weighted_loss(ptr(dist_c), dist_c.stride(0), ptr(bmu), ptr(grid_pos), B, K, k_offset,
-                                           ptr(T_dev), inv_count, ptr(scratch), ptr(loss), stream_ptr()),
+        L = _lib.lib()
+        scratch = _loss_scratch(dist_c.device, int(L.som_loss_scratch_floats(B, K)))
+        check(L.som_weighted_loss(ptr(dist_c), dist_c.stride(0), ptr(bmu), ptr(grid_pos), B, K, k_offset,
+                                  ptr(T_dev), inv_count, ptr(scratch), ptr(loss), stream_ptr()),
               "som_weighted_loss")
         ctx.save_for_backward(bmu, grid_pos, T_dev)
         ctx.shape = (B, K)
@@ -145,7 +270,7 @@ class WeightedLossFn(torch.autograd.Function):
     def backward(ctx, g_out):
         bmu, grid_pos, T_dev = ctx.saved_tensors
         B, K = ctx.shape
-        g = g_out.reshape(1).to(torch.float32).contiguous()
+        g = _grad_scalar(g_out)
         ldg = _pad4(K)
         G = torch.empty((B, ldg), device=g.device, dtype=torch.float32)
         check(_lib.lib().som_weighted_loss_grad(ptr(bmu), ptr(grid_pos), B, K, ctx.k_offset, ptr(T_dev), ptr(g),
@@ -154,26 +279,22 @@ class WeightedLossFn(torch.autograd.Function):
 
 
 class DistanceFn(torch.autograd.Function):
-    """(distances, packed minima) = f(x, W) with the closed-form backward of ATen's cdist / normalize+mm
-    (models/som_layer.py:111-125 and their autograd), both directions on the tcgen05 GEMM."""
+    """distances = f(x, W) with the closed-form backward of ATen's cdist / normalize+mm for an arbitrary upstream
+    gradient (models/som_layer.py:111-125 and their autograd).  In the training step of ViT-SOM no gradient reaches
+    this node (``FusedLossFn`` differentiates the loss directly); it serves callers that use ``distances`` in
+    their own expressions."""
 
     @staticmethod
-    def forward(ctx, x, W, mode, w_staged, idx_offset):
-        xs = StagedOperand(x, mode)
-        ws = w_staged if w_staged is not None else StagedOperand(W, mode)
-        dist, packed = fwd_distances(xs, ws, True, idx_offset)
-        ctx.mode = mode
-        ctx.xs, ctx.ws = xs, ws
-        ctx.save_for_backward(x, W, dist)
-        ctx.mark_non_differentiable(packed)
-        return dist, packed
+    def forward(ctx, x, W, state):
+        ctx.state = state
+        ctx.x_dtype, ctx.x_shape = x.dtype, x.shape
+        return state.dist_buf[:, :state.K]
 
     @staticmethod
-    def backward(ctx, g_dist, _g_packed):
-        x, W, dist = ctx.saved_tensors
-        xs, ws, mode = ctx.xs, ctx.ws, ctx.mode
-        B, K, D = xs.rows, ws.rows, xs.dim
-        dev = dist.device
+    def backward(ctx, g_dist):
+        st = ctx.state
+        B, K, D, mode = st.B, st.K, st.D, st.mode
+        dev = st.dist_buf.device
         L = _lib.lib()
         G = _rowmajor(_require_cuda_f32(g_dist, "grad_distances"))
         ldr = _pad4(K)
@@ -181,22 +302,21 @@ class DistanceFn(torch.autograd.Function):
         r_lo = torch.empty((B, ldr), device=dev, dtype=torch.float32)
         coef = torch.zeros((2 * B + 2 * K,), device=dev, dtype=torch.float32)
         ax, bx, aw, bw = coef[:B], coef[B:2 * B], coef[2 * B:2 * B + K], coef[2 * B + K:]
-        check(L.som_bwd_coeffs(ptr(G), G.stride(0), ptr(dist), dist.stride(0), B, K, mode, ptr(xs.aux), ptr(ws.aux),
+        check(L.som_bwd_coeffs(ptr(G), G.stride(0), ptr(st.dist_buf), st.ldd, B, K, mode, st.xs.aux, st.ws.aux,
                                ptr(r_hi), ptr(r_lo), ldr, ptr(ax), ptr(bx), ptr(aw), ptr(bw), stream_ptr()),
               "som_bwd_coeffs")
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            xf = _rowmajor(_require_cuda_f32(x.reshape(B, D), "x"))
             dx = torch.empty((B, D), device=dev, dtype=torch.float32)
-            check(_gemm("dx", lambda: L.som_bwd_dx(ptr(r_hi), ptr(r_lo), ldr, ptr(ws.hi), ptr(ws.lo), ws.ld, ptr(xf),
-                                                   xf.stride(0), ptr(ax), ptr(bx), B, K, D, ptr(dx), D,
+            check(_gemm("dx", lambda: L.som_bwd_dx(ptr(r_hi), ptr(r_lo), ldr, st.ws.hi, st.ws.lo, st.ws.ld, ptr(st.x),
+                                                   st.x.stride(0), ptr(ax), ptr(bx), B, K, D, ptr(dx), D,
                                                    stream_ptr())), "som_bwd_dx")
-            if dx.dtype != x.dtype:
-                dx = dx.to(x.dtype)
+            if dx.dtype != ctx.x_dtype:
+                dx = dx.to(ctx.x_dtype)
+            dx = dx.view(ctx.x_shape)
         if ctx.needs_input_grad[1]:
-            Wf = _rowmajor(_require_cuda_f32(W, "prototypes"))
             dw = torch.empty((K, D), device=dev, dtype=torch.float32)
-            check(_gemm("dw", lambda: L.som_bwd_dw(ptr(r_hi), ptr(r_lo), ldr, ptr(xs.hi), ptr(xs.lo), xs.ld, ptr(Wf),
-                                                   Wf.stride(0), ptr(aw), ptr(bw), B, K, D, ptr(dw), D,
+            check(_gemm("dw", lambda: L.som_bwd_dw(ptr(r_hi), ptr(r_lo), ldr, st.xs.hi, st.xs.lo, st.xs.ld, ptr(st.W),
+                                                   st.W.stride(0), ptr(aw), ptr(bw), B, K, D, ptr(dw), D,
                                                    stream_ptr())), "som_bwd_dw")
-        return dx, dw, None, None, None
+        return dx, dw, None

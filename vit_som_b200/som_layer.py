@@ -112,6 +112,7 @@ class SOMLayer(_Base):
         if _Base is nn.Module:
             self.trainer = None
         self._w_cache = None
+        self._dw_hook = None                                              # data-parallel wrapper: called with dW as soon as it is enqueued
 
     # ---- construction helpers -----------------------------------------------------------------
     def create_grid_positions(self):
@@ -137,43 +138,51 @@ class SOMLayer(_Base):
                 "B200 hot path; use 'euclidean' or 'cosine'")
         return ops.MODE[self.distance_fcn]
 
-    def _staged_prototypes(self, mode: int) -> ops.StagedOperand:
-        """tf32 hi/lo split (+ norms) of the prototypes, recomputed only when the parameter changed."""
+    def _staged_prototypes(self, mode: int):
+        """(staging, needs_refill): tf32 hi/lo split (+ norms) of the prototypes, refilled only when the parameter
+        changed (optimizer step, load_state_dict, .to()).  A fresh buffer is used on every refill so that a
+        backward still holding the previous staging is not overwritten."""
         W = self.prototypes
-        key = (W.data_ptr(), W._version, mode, tuple(W.shape))
-        if self._w_cache is None or self._w_cache[0] != key:
-            self._w_cache = (key, ops.StagedOperand(W.detach(), mode))
-        return self._w_cache[1]
+        key = (W.data_ptr(), W._version, mode, tuple(W.shape), W.device)
+        ws = self._w_cache
+        if ws is not None and ws.key == key:
+            return ws, False
+        ws = ops.Staging(W.shape[0], W.shape[1], mode, W.device)
+        ws.key = key
+        self._w_cache = ws
+        return ws, True
 
-    def _forward_impl(self, x):
+    def _forward_impl(self, x, want_dist=True):
         if x.dim() > 2:
             x = x.flatten(start_dim=1)
         if not x.is_cuda or not self.prototypes.is_cuda:
             raise SomError("SOMLayer runs on a B200 only: move the module and its input to cuda (no CPU path)")
-        if x.shape[1] != self.latent_dim:
-            raise ValueError(f"latent dim {x.shape[1]} != {self.latent_dim}")
+        if x.dim() != 2 or x.shape[1] != self.latent_dim:
+            raise ValueError(f"latent shape {tuple(x.shape)} does not end in latent_dim {self.latent_dim}")
         mode = self._mode()
-        ws = self._staged_prototypes(mode)
-        dist, packed = ops.DistanceFn.apply(x, self.prototypes, mode, ws, 0)
-        return dist, packed
+        ws, refill = self._staged_prototypes(mode)
+        try:
+            state, bmu = ops.forward(x, self.prototypes, mode, ws, refill, want_dist=want_dist)
+        except Exception:
+            self._w_cache = None                         # never keep a staging that may not have been filled
+            raise
+        if not want_dist:
+            return None, bmu
+        state.x_in, state.W_in = x, self.prototypes
+        dist = ops.DistanceFn.apply(x, self.prototypes, state)
+        dist._som_state = state                          # lets som_loss take the fused path (no B x K autograd edge)
+        return dist, bmu
 
     def forward(self, x):
-        distances, packed = self._forward_impl(x)
-        bmu_indices = ops.bmu_decode(packed, self.n_prototypes)
-        return distances, bmu_indices
+        return self._forward_impl(x)
 
     def compute_distances(self, x):
         return self._forward_impl(x)[0]
 
     def best_matching_units(self, x):
         """argmin-only inference path (tools/evaluation.py:29-42 keeps only the BMUs): no B x K store."""
-        if x.dim() > 2:
-            x = x.flatten(start_dim=1)
-        mode = self._mode()
         with torch.no_grad():
-            xs = ops.StagedOperand(x, mode)
-            _, packed = ops.fwd_distances(xs, self._staged_prototypes(mode), want_dist=False)
-            return ops.bmu_decode(packed, self.n_prototypes)
+            return self._forward_impl(x, want_dist=False)[1]
 
     def _temperature_tensor(self) -> torch.Tensor:
         T = self.current_temperature
@@ -204,6 +213,12 @@ class SOMLayer(_Base):
     def som_loss(self, weights, distances):
         if isinstance(weights, NeighbourhoodWeights) and weights._dense is None:
             B, K = distances.shape
+            state = getattr(distances, "_som_state", None)
+            if state is not None and state.B == B and state.K == K:
+                # distances are this layer's own forward output: loss and its backward as one node over (x, W)
+                want_grad = torch.is_grad_enabled() and (state.x_in.requires_grad or state.W_in.requires_grad)
+                return ops.FusedLossFn.apply(state.x_in, state.W_in, state, weights.bmu, self.grid_positions,
+                                             weights.T_dev, 1.0 / (B * K), 0, want_grad, self._dw_hook)
             return ops.WeightedLossFn.apply(distances, weights.bmu, self.grid_positions, weights.T_dev,
                                             1.0 / (B * K), 0)
         dense = weights.materialize() if isinstance(weights, NeighbourhoodWeights) else weights
