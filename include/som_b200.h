@@ -203,6 +203,10 @@ int som_debug_gemm(const float* a_hi, const float* a_lo, int64_t lda, int a_mn,
 
 /* Tuning knobs (process-wide): tile width override (0 = auto) and k-blocks per accumulation chunk. */
 void som_set_tuning(int bn_override, int kchunk);
+/* Kernel selection: 0 = cost model (default), 1 = single-CTA 128 x bn tiles, 2 = CTA-pair (cta_group::2) 256 x bn tiles. */
+void som_set_cta_group(int cg);
+/* Diagnostics (results are garbage): bit 0 = no TMA loads after the first ring pass, bit 1 = no tensor-core instructions. */
+void som_set_debug(int bits);
 
 #ifdef __cplusplus
 }

@@ -34,6 +34,8 @@ def run_gemm(A, Bm, a_mn, b_mn, bn=0, kchunk=0, passes=3):
     import torch
     from vit_som_b200 import _lib
     L = _lib.lib()
+    L.som_set_cta_group(int(os.environ.get("SOM_PROBE_CG", "0")))
+    L.som_set_debug(int(os.environ.get("SOM_PROBE_DEBUG", "0")))
     M, Kr = A.shape
     N = Bm.shape[0]
 
@@ -119,7 +121,7 @@ def case_timing():
     }.items():
         A = torch.randn(M, Kr, generator=g).cuda()
         Bm = torch.rand(N, Kr, generator=g).cuda()
-        for bn in (0, 128, 64):
+        for bn in [int(t) for t in os.environ.get("SOM_PROBE_BNS", "0,128,64").split(",")]:
             C = run_gemm(A, Bm, a_mn, b_mn, bn=bn)
             ref = A.double() @ Bm.double().t()
             st = err_stats(C, ref)
@@ -148,6 +150,13 @@ def case_timing():
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / iters
             st["ms"] = ms
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                h = pynvml.nvmlDeviceGetHandleByIndex(0)
+                st["sm_mhz_after"] = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            except Exception:  # noqa: BLE001
+                pass
             st["tflops_alg"] = 2.0 * M * N * Kr / ms / 1e9
             out[f"{name}_bn{bn}"] = st
     out["ok"] = True
@@ -176,6 +185,19 @@ CASES = {
     "mnmn_rand3": lambda: case_random(1, 1, 1600, 3136, 1024),
     "kmn_rand3": lambda: case_random(0, 1, 1024, 3136, 1600),
     "timing": case_timing,
+    # shapes that exercise the CTA-pair kernel (M > 128): run with --cg 2
+    "p_kk_exact_256": lambda: case_exact(0, 0, M=256, N=256, Kr=64, bn=256),
+    "p_kk_exact_128": lambda: case_exact(0, 0, M=256, N=256, Kr=64, bn=128),
+    "p_kk_exact_64": lambda: case_exact(0, 0, M=256, N=256, Kr=64, bn=64),
+    "p_kk_exact_multi": lambda: case_exact(0, 0, M=768, N=1024, Kr=512, bn=256),
+    "p_kk_exact_ragged": lambda: case_exact(0, 0, M=300, N=336, Kr=100),
+    "p_kmn_exact": lambda: case_exact(0, 1, M=256, N=256, Kr=64, bn=256),
+    "p_mnk_exact": lambda: case_exact(1, 0, M=256, N=256, Kr=64, bn=256),
+    "p_mnmn_exact": lambda: case_exact(1, 1, M=256, N=256, Kr=64, bn=256),
+    "p_mnmn_exact_ragged": lambda: case_exact(1, 1, M=300, N=336, Kr=100),
+    "p_kk_rand3_256": lambda: case_random(0, 0, 1024, 1600, 3136, bn=256),
+    "p_kk_rand3_192": lambda: case_random(0, 0, 1024, 1600, 3136, bn=192),
+    "p_kk_rand3_pos": lambda: case_random(0, 0, 512, 512, 4096, positive=True),
 }
 
 
@@ -184,7 +206,16 @@ def main():
     ap.add_argument("--case", default=None)
     ap.add_argument("--only", default=None, help="comma separated substrings: run the cases containing any")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "probe.json"))
+    ap.add_argument("--cg", type=int, default=None, help="force the kernel: 1 single-CTA, 2 CTA pair (default: cost model)")
+    ap.add_argument("--debug", type=int, default=0, help="GemmShape.debug bits (1: no TMA after prologue, 2: no MMA)")
+    ap.add_argument("--bns", default=None, help="tile widths for the timing case, e.g. 0,256,128")
     args = ap.parse_args()
+    if args.cg is not None:
+        os.environ["SOM_PROBE_CG"] = str(args.cg)
+    if args.debug:
+        os.environ["SOM_PROBE_DEBUG"] = str(args.debug)
+    if args.bns is not None:
+        os.environ["SOM_PROBE_BNS"] = args.bns
     if args.case:
         try:
             res = CASES[args.case]()

@@ -32,6 +32,8 @@ SIGNATURES = {
     "som_launch_count": (c_int64, []),
     "som_launch_count_reset": (None, []),
     "som_set_tuning": (None, [c_int, c_int]),
+    "som_set_cta_group": (None, [c_int]),
+    "som_set_debug": (None, [c_int]),
     "som_prep_rows": (c_int, [_P, c_int64, c_int64, c_int64, c_int, _P, _P, c_int64, _P, _P]),
     "som_bmu_init": (c_int, [_P, c_int64, _P]),
     "som_fwd_distances": (c_int, [_P, _P, c_int64, _P, _P, _P, c_int64, _P, c_int64, c_int64, c_int64, c_int,

@@ -15,6 +15,7 @@
 #include "som_gemm.cuh"
 
 #include <cudaTypedefs.h>
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -26,6 +27,8 @@ thread_local std::string g_last_error;
 std::atomic<int64_t> g_launches{0};
 std::atomic<int> g_bn_override{0};
 std::atomic<int> g_kchunk{16};
+std::atomic<int> g_debug{0};            // GemmShape::debug (diagnostic runs of tools/gpu_probe.py only)
+std::atomic<int> g_cg_override{0};      // 0 = cost model, 1 = single-CTA kernel, 2 = CTA-pair kernel
 
 int fail(int code, const std::string& msg) {
   g_last_error = msg;
@@ -93,34 +96,66 @@ int make_tmap(CUtensorMap* map, const float* ptr, int64_t inner, int64_t outer, 
   return SOM_OK;
 }
 
-int pick_bn(int64_t M, int64_t N, int sms, int b_mn) {
-  const int forced = g_bn_override.load();
-  if (forced) return forced;
-  if (N <= 16 && !b_mn) return 16;
-  const int cands[4] = {128, 96, 64, 32};
-  const int64_t tm = (M + som::BM - 1) / som::BM;
-  int best = 128;
-  double best_cost = 1e30;
-  for (int bn : cands) {
-    const int64_t tiles = tm * ((N + bn - 1) / bn);
-    const int64_t waves = (tiles + sms - 1) / sms;
-    const double cost = static_cast<double>(waves) * (bn + 24);   // MMA time ~ bn, fixed per-tile overhead
-    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+struct TileChoice { int cg; int bn; };
+
+// Cost model (nanoseconds) behind the tile choice, calibrated on B200 with tools/gemm_time.py:
+//  * tensor pipe: a k-block (32 deep, 12 tcgen05.mma for 3xTF32) of a 128 x bn tile per SM costs ~4.43 ns * bn at the
+//    sustained TF32 rate (822 TFLOP/s chip-wide); operands read MN-major run at ~70 % of that,
+//  * L2 -> shared memory: each CTA pulls (128 + B rows it holds) * 256 bytes of hi+lo operands per k-block; the
+//    chip delivers ~10 TB/s in total and at most ~100 GB/s into one SM,
+//  * ~6 us per wave of tiles for prologue, epilogue and launch.
+// A CTA pair halves the B rows per SM (so 256 x 256 pair tiles are tensor-bound where 128 x 128 tiles are
+// L2-bound) but needs enough tiles to keep all 74 pairs busy; small problems prefer narrower tiles.
+TileChoice pick_tile(int64_t M, int64_t N, int64_t Kred, int sms, int a_mn, int b_mn) {
+  const int forced_bn = g_bn_override.load();
+  const int forced_cg = g_cg_override.load();
+  const int64_t nkb = (Kred + som::BK - 1) / som::BK;
+  TileChoice best{1, 128};
+  double best_cost = 1e300;
+  const double mn_penalty = (a_mn || b_mn) ? 1.4 : 1.0;
+  auto consider = [&](int cg, int bn) {
+    if (forced_cg && cg != forced_cg) return;
+    if (forced_bn && bn != forced_bn) return;
+    if (cg == 2 && b_mn && (bn / 2) % 32 != 0) return;
+    const int64_t tiles = ((M + 128 * cg - 1) / (128 * cg)) * ((N + bn - 1) / bn);
+    const int64_t slots = sms / cg;
+    const int64_t waves = (tiles + slots - 1) / slots;
+    const double active_sms = static_cast<double>(tiles < slots ? tiles : slots) * cg;
+    const double gbs_per_sm = std::min(100.0, 10000.0 / active_sms);            // GB/s == bytes/ns
+    const double t_l2 = (128.0 + static_cast<double>(bn) / cg) * 256.0 / gbs_per_sm;
+    const double t_mma = 4.43 * bn * mn_penalty;
+    const double cost = static_cast<double>(waves) * (static_cast<double>(nkb) * std::max(t_mma, t_l2) + 6000.0);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = TileChoice{cg, bn}; }
+  };
+  if (N <= 16 && !b_mn) consider(1, 16);
+  for (int bn : {128, 96, 64, 32}) consider(1, bn);
+  if (M > 128 && sms >= 2)
+    for (int bn : {256, 192, 128, 64}) consider(2, bn);
+  if (best_cost >= 1e300) {                       // overrides excluded everything: honour them literally
+    best.cg = forced_cg ? forced_cg : 1;
+    best.bn = forced_bn ? forced_bn : 128;
   }
   return best;
 }
 
 template <int EPI>
 int launch_gemm_t(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi,
-                  const CUtensorMap& tb_lo, const som::GemmShape& g, const som::EpiParams& e, int grid,
+                  const CUtensorMap& tb_lo, const som::GemmShape& g, const som::EpiParams& e, int cg, int grid,
                   size_t smem, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    SOM_CUDA(cudaFuncSetAttribute(som::som_gemm3x_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  som::SMEM_LIMIT));
-    attr_set = true;
+  static bool attr_set[3] = {false, false, false};
+  if (!attr_set[cg]) {
+    if (cg == 2)
+      SOM_CUDA(cudaFuncSetAttribute(som::som_gemm3x_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    som::SMEM_LIMIT));
+    else
+      SOM_CUDA(cudaFuncSetAttribute(som::som_gemm3x_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    som::SMEM_LIMIT));
+    attr_set[cg] = true;
   }
-  som::som_gemm3x_kernel<EPI><<<grid, som::NUM_THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, g, e);
+  if (cg == 2)
+    som::som_gemm3x_pair_kernel<EPI><<<grid, som::NUM_THREADS_2CTA, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, g, e);
+  else
+    som::som_gemm3x_kernel<EPI><<<grid, som::NUM_THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, g, e);
   SOM_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
   return SOM_OK;
@@ -135,17 +170,24 @@ int launch_gemm(int epi, const float* a_hi, const float* a_lo, int64_t lda, int 
   if (M > (1ll << 30) || N > (1ll << 30) || Kred > (1ll << 30)) return fail(SOM_ERR_ARG, "GEMM dimension too large");
   if (!a_hi || !b_hi || (passes == 3 && (!a_lo || !b_lo))) return fail(SOM_ERR_ARG, "null GEMM operand");
   if (passes != 1 && passes != 3) return fail(SOM_ERR_ARG, "passes must be 1 or 3");
-  int bn = bn_req > 0 ? bn_req : pick_bn(M, N, di.sms, b_mn);
-  if (bn % 16 != 0 || bn < 16 || bn > som::MAX_BN) return fail(SOM_ERR_ARG, "tile width must be a multiple of 16 in [16,128]");
+  TileChoice tc = pick_tile(M, N, Kred, di.sms, a_mn, b_mn);
+  if (bn_req > 0) tc.bn = bn_req;
+  const int cg = tc.cg, bn = tc.bn;
+  const int max_bn = cg == 2 ? som::MAX_BN_2CTA : som::MAX_BN;
+  if (bn % 16 != 0 || bn < 16 || bn > max_bn) return fail(SOM_ERR_ARG, "tile width must be a multiple of 16 within the kernel's range");
+  if (cg == 2 && (bn % 32 != 0 || (b_mn && (bn / 2) % 32 != 0)))
+    return fail(SOM_ERR_ARG, "pair tile width must be a multiple of 32 (64 for MN-major B)");
+  const int b_rows = bn / cg;                     // rows of the B tile held by one CTA
 
   som::GemmShape g;
   g.M = static_cast<int>(M); g.N = static_cast<int>(N); g.Kred = static_cast<int>(Kred);
   g.bn = bn; g.a_mn = a_mn ? 1 : 0; g.b_mn = b_mn ? 1 : 0;
   g.kchunk = kchunk_req > 0 ? kchunk_req : g_kchunk.load();
   g.passes = passes;
-  g.tiles_m = static_cast<int>((M + som::BM - 1) / som::BM);
+  g.debug = g_debug.load();
+  g.tiles_m = static_cast<int>((M + som::BM * cg - 1) / (som::BM * cg));
   g.tiles_n = static_cast<int>((N + bn - 1) / bn);
-  const size_t b_tile = g.b_mn ? static_cast<size_t>((bn + 31) / 32) * som::PANEL_BYTES : static_cast<size_t>(bn) * som::BK * 4;
+  const size_t b_tile = g.b_mn ? static_cast<size_t>((b_rows + 31) / 32) * som::PANEL_BYTES : static_cast<size_t>(b_rows) * som::BK * 4;
   const size_t stage = 2 * som::A_TILE_BYTES + 2 * b_tile;
   const size_t fixed = 1024 /*alignment slack*/ + 8 * (2 * som::MAX_STAGES + 4) + 16;
   int nst = static_cast<int>((som::SMEM_LIMIT - fixed) / stage);
@@ -159,14 +201,15 @@ int launch_gemm(int epi, const float* a_hi, const float* a_lo, int64_t lda, int 
   if (g.a_mn) { if ((rc = make_tmap(&ta_hi, a_hi, M, Kred, lda, 32, true))) return rc; if ((rc = make_tmap(&ta_lo, a_lo ? a_lo : a_hi, M, Kred, lda, 32, true))) return rc; }
   else        { if ((rc = make_tmap(&ta_hi, a_hi, Kred, M, lda, som::BM))) return rc; if ((rc = make_tmap(&ta_lo, a_lo ? a_lo : a_hi, Kred, M, lda, som::BM))) return rc; }
   if (g.b_mn) { if ((rc = make_tmap(&tb_hi, b_hi, N, Kred, ldb, 32, true))) return rc; if ((rc = make_tmap(&tb_lo, b_lo ? b_lo : b_hi, N, Kred, ldb, 32, true))) return rc; }
-  else        { if ((rc = make_tmap(&tb_hi, b_hi, Kred, N, ldb, bn))) return rc; if ((rc = make_tmap(&tb_lo, b_lo ? b_lo : b_hi, Kred, N, ldb, bn))) return rc; }
+  else        { if ((rc = make_tmap(&tb_hi, b_hi, Kred, N, ldb, b_rows))) return rc; if ((rc = make_tmap(&tb_lo, b_lo ? b_lo : b_hi, Kred, N, ldb, b_rows))) return rc; }
 
   const int64_t nwork = static_cast<int64_t>(g.tiles_m) * g.tiles_n;
-  const int grid = static_cast<int>(nwork < di.sms ? nwork : di.sms);
+  const int64_t slots = di.sms / cg;
+  const int grid = static_cast<int>(nwork < slots ? nwork : slots) * cg;
   switch (epi) {
-    case som::EPI_RAW:  return launch_gemm_t<som::EPI_RAW>(ta_hi, ta_lo, tb_hi, tb_lo, g, e, grid, smem, st);
-    case som::EPI_DIST: return launch_gemm_t<som::EPI_DIST>(ta_hi, ta_lo, tb_hi, tb_lo, g, e, grid, smem, st);
-    case som::EPI_GRAD: return launch_gemm_t<som::EPI_GRAD>(ta_hi, ta_lo, tb_hi, tb_lo, g, e, grid, smem, st);
+    case som::EPI_RAW:  return launch_gemm_t<som::EPI_RAW>(ta_hi, ta_lo, tb_hi, tb_lo, g, e, cg, grid, smem, st);
+    case som::EPI_DIST: return launch_gemm_t<som::EPI_DIST>(ta_hi, ta_lo, tb_hi, tb_lo, g, e, cg, grid, smem, st);
+    case som::EPI_GRAD: return launch_gemm_t<som::EPI_GRAD>(ta_hi, ta_lo, tb_hi, tb_lo, g, e, cg, grid, smem, st);
   }
   return fail(SOM_ERR_ARG, "unknown epilogue");
 }
@@ -587,6 +630,8 @@ void som_set_tuning(int bn_override, int kchunk) {
   g_bn_override.store(bn_override);
   if (kchunk > 0) g_kchunk.store(kchunk);
 }
+void som_set_debug(int bits) { g_debug.store(bits); }
+void som_set_cta_group(int cg) { g_cg_override.store(cg == 1 || cg == 2 ? cg : 0); }
 
 int som_prep_rows(const float* src, int64_t rows, int64_t dim, int64_t ld_src, int mode, float* hi, float* lo,
                   int64_t ld_out, float* aux, void* stream) {
