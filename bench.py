@@ -6,8 +6,8 @@ A *step* is one pass of the hot path over one synthetic batch: operand staging (
 change every training step) -> tcgen05 distance GEMM + argmin -> neighbourhood-weighted loss -> backward
 (R staging + the two gradient GEMMs) -> for N > 1 the prototype-gradient all-reduce (batch-sharded data
 parallel, weak scaling: every rank owns a full batch).  Inputs are resident in HBM for `value`; `e2e` repeats
-the measurement through the public module API with the batch coming from pinned host memory each step and the
-loss read back.  L2 is flushed between timed steps.  One JSON line is printed by rank 0.
+the measurement through the public module API with the batch coming from pinned host memory each step (copied on a
+side stream, double buffered) and the loss read back.  L2 is flushed between the timed steps of `value`.  One JSON line is printed by rank 0.
 
 `--impl reference` times the reference's CPU implementation of the same step on the host cores (the unmodified
 reference module when /root/reference is present, else oracle/som_torch_ref.py which issues the same ATen calls).
@@ -234,21 +234,29 @@ def main():
     torch.manual_seed(1234 + rank)
     layer = SOMLayer(make_cfg(ms, D, fcn, T)).to(dev)
     layer.current_temperature = T
-    if world > 1:
-        dist.broadcast(layer.prototypes.data, 0)
     chunk = min(B, 8192)                       # cfg5: rows processed in chunks so the B x K scratch stays bounded
     x_dev = torch.randn(B, D, device=dev, requires_grad=True)
     x_host = torch.randn(B, D).pin_memory()
-    x_stage = torch.empty(B, D, device=dev, requires_grad=True)
+    x_stage = [torch.empty(B, D, device=dev, requires_grad=True) for _ in range(2)]
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    comm_stream = torch.cuda.Stream(dev) if world > 1 else None
+    copy_stream = torch.cuda.Stream(dev)
+
+    dp = None
+    if world > 1:                              # batch-sharded DP: prototype-gradient all-reduce over NVLink,
+        from vit_som_b200.distributed import DataParallelSOM
+        dp = DataParallelSOM(layer)            # issued on a side stream from inside backward (runs under the dx GEMM)
 
     def hot_path(x):
         """One step through the public module API (vit_som.py:82-86 call sequence + backward)."""
         layer._w_cache = None                  # prototypes change every training step: their staging is in the step
         layer.prototypes.grad = None
         x.grad = None
+        if chunk >= B:
+            d, bmu = layer(x)
+            loss = layer.som_loss(layer.compute_weights(bmu), d)
+            loss.backward()
+            return loss.detach()
         total = None
         for r0 in range(0, B, chunk):
             xc = x[r0:r0 + chunk]
@@ -256,9 +264,6 @@ def main():
             loss = layer.som_loss(layer.compute_weights(bmu), d) * (xc.shape[0] / B)
             loss.backward()
             total = loss.detach() if total is None else total + loss.detach()
-        if world > 1:                          # batch-sharded DP: prototype-gradient all-reduce over NVLink
-            dist.all_reduce(layer.prototypes.grad)
-            layer.prototypes.grad.div_(world)
         return total
 
     def barrier():
@@ -304,19 +309,37 @@ def main():
         gemm_ms.setdefault(name, []).append(s.elapsed_time(e))
     ops.GEMM_TIMERS = None
 
-    # ---- end to end: batch from pinned host memory every step, loss read back ----
-    e2e_evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K_)]
+    # ---- end to end: every step's batch comes from pinned host memory, the loss is read back ----
+    # The copy of batch i+1 is issued on a copy stream while step i computes (double-buffered staging, what a
+    # data loader with a prefetch queue does); all K copies and all K read-backs lie inside the timed window.
+    main_stream = torch.cuda.current_stream(dev)
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(j):
+        copy_stream.wait_event(consumed[j])            # the step that last read this buffer has finished
+        with torch.cuda.stream(copy_stream), torch.no_grad():
+            x_stage[j].copy_(x_host, non_blocking=True)
+        copied[j].record(copy_stream)
+
+    for j in range(2):
+        consumed[j].record(main_stream)
+    e2e_start, e2e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    flush_buf.zero_()
+    e2e_start.record()
+    prefetch(0)
     for i in range(K_):
-        flush_buf.zero_()
-        e2e_evs[i][0].record()
-        with torch.no_grad():
-            x_stage.copy_(x_host, non_blocking=True)
-        loss = hot_path(x_stage)
+        j = i & 1
+        if i + 1 < K_:
+            prefetch(j ^ 1)
+        main_stream.wait_event(copied[j])
+        loss = hot_path(x_stage[j])
+        consumed[j].record(main_stream)
         loss_host.copy_(loss, non_blocking=True)
-        e2e_evs[i][1].record()
+    e2e_end.record()
     barrier()
-    e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_evs)
+    e2e_ms = e2e_start.elapsed_time(e2e_end)
 
     if world > 1:
         t = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)

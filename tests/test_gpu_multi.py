@@ -1,0 +1,124 @@
+"""Multi-GPU parity (needs >= 2 B200s: ``gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu``).
+
+One process per GPU over NCCL.  The prototype-sharded layer and the batch-sharded data-parallel wrapper are compared
+with the CPU oracle's single-process answer on the full problem (tolerances of BASELINE.json: BMU exact up to fp32
+near-ties, loss / gradients 1e-5 relative).
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import som_oracle as O
+from oracle.ref_import import make_config
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _run(rank, world, port, fn, args):
+    import datetime
+    import traceback
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank),
+                            timeout=datetime.timedelta(seconds=90))
+    try:
+        fn(rank, world, *args)
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
+    except BaseException:  # noqa: BLE001
+        # a failed rank must not wait for its peer inside a collective or in destroy_process_group: leave at once
+        traceback.print_exc()
+        os._exit(1)
+
+
+def spawn(fn, *args, world=2):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.spawn(_run, args=(world, _free_port(), fn, args), nprocs=world, join=False)
+    import time
+    deadline = time.time() + 240
+    while not ctx.join(timeout=5):                       # raises if a rank failed (and terminates the others)
+        if time.time() > deadline:
+            for p in ctx.processes:
+                p.kill()
+            pytest.fail("multi-GPU worker timed out")
+
+
+def _sharded_worker(rank, world, fcn):
+    from vit_som_b200.distributed import PrototypeShardedSOM, shard_range
+    ms, D, B, T = (24, 20), 160, 333, 3.0
+    K = ms[0] * ms[1]
+    torch.manual_seed(7)                                  # same seed on every rank: identical full-map draw
+    layer = PrototypeShardedSOM(make_config(list(ms), D, fcn, Tmax=T)).cuda()
+    torch.manual_seed(7)
+    W_full = torch.rand(K, D)
+    if fcn == "cosine":
+        W_full = torch.nn.functional.normalize(W_full, p=2, dim=1)
+    k0, k1 = shard_range(K, world, rank)
+    x_np = np.random.RandomState(1).randn(B, D).astype(np.float32)
+    x = torch.as_tensor(x_np).cuda().requires_grad_(True)
+    d_loc, bmu = layer(x)
+    loss = layer.som_loss(layer.compute_weights(bmu), d_loc)
+    (loss * 0.5).backward()
+    bmu_only = layer.best_matching_units(x)                # last collective: every check below is local
+    torch.cuda.synchronize()
+    assert torch.equal(layer.prototypes.detach().cpu(), W_full[k0:k1])
+    assert d_loc.shape == (B, k1 - k0)
+    pos = O.grid_positions(ms)
+    ref = O.step(x_np, W_full.numpy(), pos, T, fcn, 0.5, np.float64, bmu_override=bmu.cpu().numpy())
+    _, hard, worst = O.classify_bmu_mismatches(x_np, W_full.numpy(), bmu.cpu().numpy(), fcn)
+    assert hard == 0, worst
+    assert O.rel_err(d_loc.detach().cpu().numpy(), ref.distances[:, k0:k1]) < 3e-6
+    assert abs(loss.item() - float(ref.loss)) <= 1e-5 * abs(float(ref.loss))
+    assert O.rel_err(x.grad.cpu().numpy(), ref.grad_x) < 1e-5
+    assert O.rel_err(layer.prototypes.grad.cpu().numpy(), ref.grad_w[k0:k1]) < 1e-5
+    assert torch.equal(bmu, bmu_only)
+
+
+@pytest.mark.parametrize("fcn", ["euclidean", "cosine"])
+def test_prototype_sharded_matches_oracle(fcn):
+    spawn(_sharded_worker, fcn)
+
+
+def _dp_worker(rank, world, fcn):
+    from vit_som_b200 import SOMLayer
+    from vit_som_b200.distributed import DataParallelSOM
+    ms, D, B, T = (12, 12), 200, 192, 2.5
+    torch.manual_seed(50 + rank)                          # different initial prototypes: the wrapper broadcasts rank 0's
+    layer = SOMLayer(make_config(list(ms), D, fcn, Tmax=T)).cuda()
+    DataParallelSOM(layer)
+    W = layer.prototypes.detach().cpu().numpy()
+    x_np = np.random.RandomState(2).randn(B, D).astype(np.float32)
+    r0, r1 = rank * B // world, (rank + 1) * B // world
+    x = torch.as_tensor(x_np[r0:r1]).cuda().requires_grad_(True)
+    d, bmu = layer(x)
+    loss = layer.som_loss(layer.compute_weights(bmu), d)
+    loss.backward()
+    import torch.distributed as dist
+    gathered = [torch.empty_like(layer.prototypes.grad) for _ in range(world)]
+    dist.all_gather(gathered, layer.prototypes.grad)       # last collective: every check below is local
+    torch.cuda.synchronize()
+    pos = O.grid_positions(ms)
+    full_bmu = O.bmu(O.distances(x_np, W, fcn, np.float64))
+    loc = O.step(x_np[r0:r1], W, pos, T, fcn, 1.0, np.float64, bmu_override=bmu.cpu().numpy())
+    ref = O.step(x_np, W, pos, T, fcn, 1.0, np.float64)
+    assert O.rel_err(x.grad.cpu().numpy(), loc.grad_x) < 1e-5              # dx stays local (scaled by the local mean)
+    if (bmu.cpu().numpy() == full_bmu[r0:r1]).all():
+        assert O.rel_err(layer.prototypes.grad.cpu().numpy(), ref.grad_w) < 1e-5   # averaged dW = global-batch dW
+    assert all(torch.equal(g, gathered[0]) for g in gathered)              # every rank holds the same averaged gradient
+
+
+@pytest.mark.parametrize("fcn", ["euclidean", "cosine"])
+def test_data_parallel_matches_oracle(fcn):
+    spawn(_dp_worker, fcn)

@@ -497,7 +497,11 @@ bwd_coeffs_kernel(const float* __restrict__ G, long long ldg, const float* __res
 //   * its row / column sums (the rank-1 coefficients of the closed-form backward).
 // The upstream gradient g_out multiplies the result in the epilogue of the gradient GEMMs, so backward needs no
 // further pass over B x K.  r_hi == nullptr: loss only (validation / no_grad).
-// thread <-> column k, loop over COEFF_ROWS rows: coalesced reads of dist, coalesced writes of R.
+// Block = 16 rows x 512 columns: warp (rh, cs) owns 8 rows x 128 columns, a lane 4 consecutive columns (one
+// 16-byte load of dist, two 16-byte stores of R per row); row sums by warp shuffle, column sums in registers.
+constexpr int LC_ROWS = 16;
+constexpr int LC_COLS = 512;
+
 __global__ void __launch_bounds__(256)
 loss_coeffs_kernel(const float* __restrict__ dist, long long ldd, const long long* __restrict__ bmu,
                    const float* __restrict__ pos, long long B, long long K, long long k_offset,
@@ -505,71 +509,91 @@ loss_coeffs_kernel(const float* __restrict__ dist, long long ldd, const long lon
                    float* __restrict__ r_hi, float* __restrict__ r_lo, long long ldr,
                    float* __restrict__ row_sum, float* __restrict__ col_sum,
                    float* __restrict__ partials, float* __restrict__ loss_out) {
-  const long long k = static_cast<long long>(blockIdx.y) * 256 + threadIdx.x;
-  const long long b0 = static_cast<long long>(blockIdx.x) * COEFF_ROWS;
-  const bool col_ok = k < K;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rh = warp >> 2, cs = warp & 3;
+  const long long k0 = static_cast<long long>(blockIdx.y) * LC_COLS + cs * 128 + lane * 4;
+  const long long b0 = static_cast<long long>(blockIdx.x) * LC_ROWS + rh * 8;
   const bool want_r = r_hi != nullptr;
-  __shared__ float red[COEFF_ROWS][8];
-  __shared__ float2 pb[COEFF_ROWS];
+  const bool vec = (ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(dist) & 15) == 0 &&
+                   (!want_r || ((ldr & 3) == 0 && ((reinterpret_cast<uintptr_t>(r_hi) | reinterpret_cast<uintptr_t>(r_lo)) & 15) == 0));
   __shared__ float lred[8];
   __shared__ double dred[256];
   __shared__ bool is_last;
-  if (threadIdx.x < COEFF_ROWS) {
-    const long long b = b0 + threadIdx.x;
-    float2 p = make_float2(0.f, 0.f);
-    if (b < B) p = __ldg(reinterpret_cast<const float2*>(pos) + bmu[b]);
-    pb[threadIdx.x] = p;
-  }
+
+  // BMU grid position of this warp's 8 rows: lane r loads row r, broadcast by shuffle in the loop
+  float2 pbv = make_float2(0.f, 0.f);
+  if (lane < 8 && b0 + lane < B) pbv = __ldg(reinterpret_cast<const float2*>(pos) + bmu[b0 + lane]);
   const float T = __ldg(T_dev);
   const float two_t2 = 2.f * (T * T);
-  const float2 pk = col_ok ? __ldg(reinterpret_cast<const float2*>(pos) + k_offset + k) : make_float2(0.f, 0.f);
-  __syncthreads();
-  float colsum = 0.f, lsum = 0.f;
-#pragma unroll 4
-  for (int r = 0; r < COEFF_ROWS; ++r) {
+  float2 pk[4];
+  bool ok[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    ok[i] = k0 + i < K;
+    pk[i] = ok[i] ? __ldg(reinterpret_cast<const float2*>(pos) + k_offset + k0 + i) : make_float2(0.f, 0.f);
+  }
+  float colsum[4] = {0.f, 0.f, 0.f, 0.f};
+  float lsum = 0.f;
+#pragma unroll 2
+  for (int r = 0; r < 8; ++r) {
     const long long b = b0 + r;
-    float rowterm = 0.f;
-    if (b < B && col_ok) {
-      const float d = __ldg(dist + b * ldd + k);
-      const float w = neighbourhood_weight(pk.x, pk.y, pb[r].x, pb[r].y, two_t2);
-      lsum = fmaf(w, d, lsum);
-      if (want_r) {
-        const float g = inv_count * w;
-        float rv, term;
-        if (mode == 0) {
-          rv = (d == 0.f) ? 0.f : g / d;               // ATen: ratio.masked_fill_(dist == 0, 0)
-          term = rv;
-        } else {
-          rv = g;
-          term = g * (1.f - d);                        // g * (x^ . w^): projection coefficient of normalize backward
+    const float pby = __shfl_sync(0xffffffffu, pbv.x, r), pbx = __shfl_sync(0xffffffffu, pbv.y, r);
+    if (b >= B) break;                                   // warp-uniform
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ok[0]) {
+      if (vec) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(dist + b * ldd + k0));
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if (ok[i]) d[i] = __ldg(dist + b * ldd + k0 + i);
+      }
+    }
+    float h[4], l[4], rowterm = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      h[i] = 0.f; l[i] = 0.f;
+      if (ok[i]) {
+        const float w = neighbourhood_weight(pk[i].x, pk[i].y, pby, pbx, two_t2);
+        lsum = fmaf(w, d[i], lsum);
+        if (want_r) {
+          const float g = inv_count * w;
+          float rv, term;
+          if (mode == 0) {
+            rv = (d[i] == 0.f) ? 0.f : g / d[i];         // ATen: ratio.masked_fill_(dist == 0, 0)
+            term = rv;
+          } else {
+            rv = g;
+            term = g * (1.f - d[i]);                     // g * (x^ . w^): projection coefficient of normalize backward
+          }
+          h[i] = tf32_rna(rv);
+          l[i] = tf32_rna(rv - h[i]);
+          colsum[i] += term;
+          rowterm += term;
         }
-        const float h = tf32_rna(rv);
-        r_hi[b * ldr + k] = h;
-        r_lo[b * ldr + k] = tf32_rna(rv - h);
-        colsum += term;
-        rowterm = term;
       }
     }
     if (want_r) {
+      if (ok[0]) {
+        if (vec) {
+          *reinterpret_cast<float4*>(r_hi + b * ldr + k0) = make_float4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<float4*>(r_lo + b * ldr + k0) = make_float4(l[0], l[1], l[2], l[3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) if (ok[i]) { r_hi[b * ldr + k0 + i] = h[i]; r_lo[b * ldr + k0 + i] = l[i]; }
+        }
+      }
       rowterm = warp_sum(rowterm);
-      if ((threadIdx.x & 31) == 0) red[r][threadIdx.x >> 5] = rowterm;
+      if (lane == 0) atomicAdd(row_sum + b, rowterm);
     }
+  }
+  if (want_r) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) if (ok[i]) atomicAdd(col_sum + k0 + i, colsum[i]);
   }
   lsum = warp_sum(lsum);
-  if ((threadIdx.x & 31) == 0) lred[threadIdx.x >> 5] = lsum;
+  if (lane == 0) lred[warp] = lsum;
   __syncthreads();
-  if (want_r) {
-    if (threadIdx.x < COEFF_ROWS) {
-      const long long b = b0 + threadIdx.x;
-      if (b < B) {
-        float t = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) t += red[threadIdx.x][i];
-        atomicAdd(row_sum + b, t);
-      }
-    }
-    if (col_ok) atomicAdd(col_sum + k, colsum);
-  }
   // deterministic loss: per-block partial, last block reduces all partials in a fixed order in fp64
   const long long nblocks = static_cast<long long>(gridDim.x) * gridDim.y;
   unsigned int* counter = reinterpret_cast<unsigned int*>(partials);
@@ -805,7 +829,7 @@ int som_loss_fused(const float* dist, int64_t ldd, const int64_t* bmu, const flo
     SOM_CUDA(cudaMemsetAsync(row_sum, 0, sizeof(float) * B, as_stream(stream)));
     SOM_CUDA(cudaMemsetAsync(col_sum, 0, sizeof(float) * K, as_stream(stream)));
   }
-  dim3 grid(static_cast<unsigned>((B + COEFF_ROWS - 1) / COEFF_ROWS), static_cast<unsigned>((K + 255) / 256));
+  dim3 grid(static_cast<unsigned>((B + LC_ROWS - 1) / LC_ROWS), static_cast<unsigned>((K + LC_COLS - 1) / LC_COLS));
   loss_coeffs_kernel<<<grid, 256, 0, as_stream(stream)>>>(dist, ldd, reinterpret_cast<const long long*>(bmu), grid_pos,
                                                          B, K, k_offset, T_dev, inv_count, mode, r_hi, r_lo, ldr,
                                                          row_sum, col_sum, scratch, loss_out);
@@ -815,7 +839,7 @@ int som_loss_fused(const float* dist, int64_t ldd, const int64_t* bmu, const flo
 }
 
 int64_t som_loss_fused_scratch_floats(int64_t B, int64_t K) {
-  return ((B + COEFF_ROWS - 1) / COEFF_ROWS) * ((K + 255) / 256) + 2;
+  return ((B + LC_ROWS - 1) / LC_ROWS) * ((K + LC_COLS - 1) / LC_COLS) + 2;
 }
 
 int som_backward_dw(const float* r_hi, const float* r_lo, int64_t ldr, const float* x_hi, const float* x_lo,
