@@ -49,6 +49,10 @@ int device_info(DeviceInfo& out) {
   int dev = 0;
   SOM_CUDA(cudaGetDevice(&dev));
   if (dev != cached_dev) {
+    // First call on this thread for this device: bind the primary context.  PyTorch's autograd worker threads
+    // may reach us before any runtime call of theirs has done so, and cuTensorMapEncodeTiled (a driver entry point)
+    // fails with CUDA_ERROR_INVALID_CONTEXT on a thread without a current context.
+    SOM_CUDA(cudaFree(nullptr));
     DeviceInfo d;
     SOM_CUDA(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
     SOM_CUDA(cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
