@@ -272,6 +272,12 @@ def main():
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    # Everything below runs on a high-priority compute stream, so that under data parallelism the (lowest-priority)
+    # communication stream of DataParallelSOM only takes SMs the GEMMs leave free.
+    compute_stream = torch.cuda.Stream(dev, priority=-1)
+    compute_stream.wait_stream(torch.cuda.current_stream(dev))
+    torch.cuda.set_stream(compute_stream)
+
     # ---- warm-up ----
     for _ in range(W_):
         hot_path(x_dev)

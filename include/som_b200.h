@@ -44,6 +44,16 @@ extern "C" {
 #define SOM_ERR_CUDA      -2   /* a CUDA runtime / driver call failed                            */
 #define SOM_ERR_DEVICE    -3   /* device is not sm_100 (Blackwell B200) - there is no fallback   */
 
+/*
+ * GEMM workspace.  Every entry point that launches the tensor-core GEMM takes `ws` / `ws_floats`: an optional,
+ * 16-byte aligned device scratch buffer owned by the caller (one per stream in flight).  With it the CTA-pair
+ * kernel may schedule stream-K (partial accumulators + a fix-up kernel) when whole tiles would leave SMs idle;
+ * ws == NULL keeps the classic one-tile-per-CTA schedule.  som_gemm_workspace_floats() floats always suffice.
+ */
+int64_t som_gemm_workspace_floats(void);
+/* Stream-K policy: -1 never, 0 cost model (default), 1 whenever a workspace is available and the shape allows. */
+void som_set_streamk(int mode);
+
 /* ABI version, bumped on any signature change. */
 int som_b200_abi_version(void);
 
@@ -80,7 +90,8 @@ int som_bmu_init(long long* packed, int64_t B, void* stream);
 int som_fwd_distances(const float* x_hi, const float* x_lo, int64_t ldx, const float* x_aux,
                       const float* w_hi, const float* w_lo, int64_t ldw, const float* w_aux,
                       int64_t B, int64_t K, int64_t D, int mode, int64_t idx_offset,
-                      float* dist, int64_t ldd, long long* packed, void* stream);
+                      float* dist, int64_t ldd, long long* packed,
+                      float* ws, int64_t ws_floats, void* stream);
 
 /* bmu[b] = low 32 bits of packed[b] (clamped to [0, K_total)), optional min_key[b] = winning key. */
 int som_bmu_decode(const long long* packed, int64_t B, int64_t K_total,
@@ -128,13 +139,15 @@ int som_bwd_coeffs(const float* G, int64_t ldg, const float* dist, int64_t ldd,
 int som_bwd_dx(const float* r_hi, const float* r_lo, int64_t ldr,
                const float* w_hi, const float* w_lo, int64_t ldw,
                const float* x, int64_t ldx, const float* ax, const float* bx,
-               int64_t B, int64_t K, int64_t D, float* dx, int64_t lddx, void* stream);
+               int64_t B, int64_t K, int64_t D, float* dx, int64_t lddx,
+               float* ws, int64_t ws_floats, void* stream);
 
 /* dw[K,D] = aw[k] * w[k,:] - bw[k] * sum_b R[b,k] x~[b,:]   (R and x~ read MN-major). */
 int som_bwd_dw(const float* r_hi, const float* r_lo, int64_t ldr,
                const float* x_hi, const float* x_lo, int64_t ldx,
                const float* w, int64_t ldw, const float* aw, const float* bw,
-               int64_t B, int64_t K, int64_t D, float* dw, int64_t lddw, void* stream);
+               int64_t B, int64_t K, int64_t D, float* dw, int64_t lddw,
+               float* ws, int64_t ws_floats, void* stream);
 
 /*
  * ---- Fused protocol entry points: one call per stage of the reference's call sequence ----------------
@@ -152,7 +165,7 @@ int som_forward(const float* x, int64_t ldx, const float* W, int64_t ldw,
                 int64_t B, int64_t K, int64_t D, int mode, int stage_w, int64_t idx_offset,
                 float* x_hi, float* x_lo, float* x_aux, float* w_hi, float* w_lo, float* w_aux,
                 int64_t ld_stage, float* dist, int64_t ldd, long long* packed, int64_t* bmu,
-                int64_t K_total, void* stream);
+                int64_t K_total, float* ws, int64_t ws_floats, void* stream);
 
 /*
  * som_loss_fused = compute_weights + som_loss (models/som_layer.py:137-152) and, when r_hi != NULL, the
@@ -181,12 +194,14 @@ int som_backward_dw(const float* r_hi, const float* r_lo, int64_t ldr,
                     const float* x_hi, const float* x_lo, int64_t ld_stage,
                     const float* W, int64_t ldw, const float* col_sum, const float* w_aux,
                     const float* g_dev, int64_t B, int64_t K, int64_t D, int mode,
-                    float* dW, int64_t lddw, int accumulate, void* stream);
+                    float* dW, int64_t lddw, int accumulate,
+                    float* ws, int64_t ws_floats, void* stream);
 int som_backward_dx(const float* r_hi, const float* r_lo, int64_t ldr,
                     const float* w_hi, const float* w_lo, int64_t ld_stage,
                     const float* x, int64_t ldx, const float* row_sum, const float* x_aux,
                     const float* g_dev, int64_t B, int64_t K, int64_t D, int mode,
-                    float* dx, int64_t lddx, int accumulate, void* stream);
+                    float* dx, int64_t lddx, int accumulate,
+                    float* ws, int64_t ws_floats, void* stream);
 
 /*
  * Diagnostic entry point (used by the tests to validate the tensor-core mainloop in isolation):
@@ -199,7 +214,7 @@ int som_backward_dx(const float* r_hi, const float* r_lo, int64_t ldr,
 int som_debug_gemm(const float* a_hi, const float* a_lo, int64_t lda, int a_mn,
                    const float* b_hi, const float* b_lo, int64_t ldb, int b_mn,
                    int64_t M, int64_t N, int64_t Kred, int bn, int kchunk, int passes,
-                   float* C, int64_t ldc, void* stream);
+                   float* C, int64_t ldc, float* ws, int64_t ws_floats, void* stream);
 
 /* Tuning knobs (process-wide): tile width override (0 = auto) and k-blocks per accumulation chunk. */
 void som_set_tuning(int bn_override, int kchunk);
@@ -207,6 +222,10 @@ void som_set_tuning(int bn_override, int kchunk);
 void som_set_cta_group(int cg);
 /* Diagnostics (results are garbage): bit 0 = no TMA loads after the first ring pass, bit 1 = no tensor-core instructions. */
 void som_set_debug(int bits);
+/* Diagnostics: device buffer of 8 uint64 in which CTA 0 of the pair kernel stamps %globaltimer (ns) at its phase
+ * boundaries (start, setup done, producer done, issuer done, last accumulators ready, epilogue done, pair synced,
+ * TMEM freed); NULL switches it off. */
+void som_set_debug_times(unsigned long long* dev_buf);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,66 @@
+"""The C-ABI boundary without a GPU: the library builds for sm_100a, loads, exports every symbol that
+include/som_b200.h declares, the ctypes signatures mirror the header argument for argument, and the entry points
+fail loudly (no fallback) when there is no B200."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "som_b200.h")
+
+
+def declared_functions():
+    """{name: number of parameters} parsed from the header (comments stripped)."""
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    out = {}
+    for m in re.finditer(r"\b(?:int|int64_t|void|const char\*)\s+(som_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        name, params = m.group(1), m.group(2).strip()
+        out[name] = 0 if params in ("", "void") else params.count(",") + 1
+    return out
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from vit_som_b200 import _lib
+    _lib.build()                       # no-op when libsom_b200.so is newer than its sources
+    return _lib.lib()
+
+
+def test_header_symbols_are_exported_and_bound(lib):
+    from vit_som_b200 import _lib
+    decl = declared_functions()
+    assert len(decl) >= 25 and "som_forward" in decl and "som_backward_dx" in decl
+    for name, nparams in decl.items():
+        assert hasattr(lib, name), f"{name} is declared in som_b200.h but not exported by libsom_b200.so"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in vit_som_b200/_lib.py"
+        assert len(_lib.SIGNATURES[name][1]) == nparams, f"{name}: header has {nparams} parameters"
+    for name in _lib.SIGNATURES:
+        assert name in decl, f"{name} is bound in _lib.py but not declared in include/som_b200.h"
+
+
+def test_abi_version_and_pure_host_entry_points(lib):
+    assert lib.som_b200_abi_version() == 3
+    assert lib.som_gemm_workspace_floats() == 2 * 74 * 256 * 256
+    assert lib.som_loss_scratch_floats(1024, 1600) >= 1024 * 2
+    assert lib.som_loss_fused_scratch_floats(1024, 1600) == (1024 // 16) * 4 + 2
+    lib.som_launch_count_reset()
+    assert lib.som_launch_count() == 0
+
+
+def test_no_gpu_means_loud_failure_not_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("this check is for the GPU-less build container")
+    buf = (ctypes.c_float * 16)()
+    rc = lib.som_prep_rows(ctypes.addressof(buf), 1, 4, 4, 0, ctypes.addressof(buf), ctypes.addressof(buf), 4,
+                           ctypes.addressof(buf), None)
+    assert rc != 0 and lib.som_last_error()
+    from vit_som_b200 import SOMLayer, SomError
+    from oracle.ref_import import make_config
+    layer = SOMLayer(make_config([4, 4], 8))
+    with pytest.raises(SomError):
+        layer(torch.randn(3, 8))

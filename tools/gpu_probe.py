@@ -17,6 +17,20 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+WS = None      # GEMM workspace (stream-K); allocated when SOM_PROBE_SK is set
+
+
+def _setup_streamk(L):
+    global WS
+    import torch
+    mode = os.environ.get("SOM_PROBE_SK")
+    if mode is None:
+        return
+    L.som_set_streamk(int(mode))
+    if WS is None and int(mode) >= 0:
+        WS = torch.empty(int(L.som_gemm_workspace_floats()), device="cuda")
+
+
 def split_tf32(x):
     """Exact tf32 hi/lo split with round-to-nearest-away (cvt.rna.tf32.f32)."""
     import torch
@@ -36,6 +50,7 @@ def run_gemm(A, Bm, a_mn, b_mn, bn=0, kchunk=0, passes=3):
     L = _lib.lib()
     L.som_set_cta_group(int(os.environ.get("SOM_PROBE_CG", "0")))
     L.som_set_debug(int(os.environ.get("SOM_PROBE_DEBUG", "0")))
+    _setup_streamk(L)
     M, Kr = A.shape
     N = Bm.shape[0]
 
@@ -57,7 +72,7 @@ def run_gemm(A, Bm, a_mn, b_mn, bn=0, kchunk=0, passes=3):
     b_hi, b_lo, ldb = stage(Bm, b_mn)
     C = torch.full((M, N), float("nan"), device="cuda")
     rc = L.som_debug_gemm(a_hi.data_ptr(), a_lo.data_ptr(), lda, a_mn, b_hi.data_ptr(), b_lo.data_ptr(), ldb, b_mn,
-                          M, N, Kr, bn, kchunk, passes, C.data_ptr(), N, _lib.stream_ptr())
+                          M, N, Kr, bn, kchunk, passes, C.data_ptr(), N, WS.data_ptr() if WS is not None else None, WS.numel() if WS is not None else 0, _lib.stream_ptr())
     _lib.check(rc, "som_debug_gemm")
     torch.cuda.synchronize()
     return C
@@ -128,6 +143,7 @@ def case_timing():
             # timing: re-stage once, launch many
             from vit_som_b200 import _lib
             L = _lib.lib()
+            _setup_streamk(L)
 
             def stage(X, mn):
                 src = X.t().contiguous() if mn else X
@@ -139,13 +155,13 @@ def case_timing():
             s = _lib.stream_ptr()
             for _ in range(3):
                 L.som_debug_gemm(a_hi.data_ptr(), a_lo.data_ptr(), lda, a_mn, b_hi.data_ptr(), b_lo.data_ptr(), ldb,
-                                 b_mn, M, N, Kr, bn, 0, 3, Cb.data_ptr(), N, s)
+                                 b_mn, M, N, Kr, bn, 0, 3, Cb.data_ptr(), N, WS.data_ptr() if WS is not None else None, WS.numel() if WS is not None else 0, s)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             iters = 20
             for _ in range(iters):
                 L.som_debug_gemm(a_hi.data_ptr(), a_lo.data_ptr(), lda, a_mn, b_hi.data_ptr(), b_lo.data_ptr(), ldb,
-                                 b_mn, M, N, Kr, bn, 0, 3, Cb.data_ptr(), N, s)
+                                 b_mn, M, N, Kr, bn, 0, 3, Cb.data_ptr(), N, WS.data_ptr() if WS is not None else None, WS.numel() if WS is not None else 0, s)
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / iters
@@ -208,10 +224,13 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "probe.json"))
     ap.add_argument("--cg", type=int, default=None, help="force the kernel: 1 single-CTA, 2 CTA pair (default: cost model)")
     ap.add_argument("--debug", type=int, default=0, help="GemmShape.debug bits (1: no TMA after prologue, 2: no MMA)")
+    ap.add_argument("--sk", type=int, default=None, help="stream-K policy with a workspace: -1 never, 0 cost model, 1 always")
     ap.add_argument("--bns", default=None, help="tile widths for the timing case, e.g. 0,256,128")
     args = ap.parse_args()
     if args.cg is not None:
         os.environ["SOM_PROBE_CG"] = str(args.cg)
+    if args.sk is not None:
+        os.environ["SOM_PROBE_SK"] = str(args.sk)
     if args.debug:
         os.environ["SOM_PROBE_DEBUG"] = str(args.debug)
     if args.bns is not None:

@@ -34,10 +34,13 @@ SIGNATURES = {
     "som_set_tuning": (None, [c_int, c_int]),
     "som_set_cta_group": (None, [c_int]),
     "som_set_debug": (None, [c_int]),
+    "som_set_debug_times": (None, [_P]),
     "som_prep_rows": (c_int, [_P, c_int64, c_int64, c_int64, c_int, _P, _P, c_int64, _P, _P]),
     "som_bmu_init": (c_int, [_P, c_int64, _P]),
     "som_fwd_distances": (c_int, [_P, _P, c_int64, _P, _P, _P, c_int64, _P, c_int64, c_int64, c_int64, c_int,
-                                  c_int64, _P, c_int64, _P, _P]),
+                                  c_int64, _P, c_int64, _P, _P, c_int64, _P]),
+    "som_gemm_workspace_floats": (c_int64, []),
+    "som_set_streamk": (None, [c_int]),
     "som_bmu_decode": (c_int, [_P, c_int64, c_int64, _P, _P, _P]),
     "som_neighbourhood": (c_int, [_P, _P, c_int64, c_int64, c_int64, _P, _P, c_int64, _P]),
     "som_loss_scratch_floats": (c_int64, [c_int64, c_int64]),
@@ -46,20 +49,20 @@ SIGNATURES = {
     "som_bwd_coeffs": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int64, c_int, _P, _P, _P, _P, c_int64,
                                _P, _P, _P, _P, _P]),
     "som_bwd_dx": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, c_int64, _P, _P, c_int64, c_int64, c_int64,
-                           _P, c_int64, _P]),
+                           _P, c_int64, _P, c_int64, _P]),
     "som_bwd_dw": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, c_int64, _P, _P, c_int64, c_int64, c_int64,
-                           _P, c_int64, _P]),
+                           _P, c_int64, _P, c_int64, _P]),
     "som_forward": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int64,
-                            _P, _P, _P, _P, _P, _P, c_int64, _P, c_int64, _P, _P, c_int64, _P]),
+                            _P, _P, _P, _P, _P, _P, c_int64, _P, c_int64, _P, _P, c_int64, _P, c_int64, _P]),
     "som_loss_fused_scratch_floats": (c_int64, [c_int64, c_int64]),
     "som_loss_fused": (c_int, [_P, c_int64, _P, _P, c_int64, c_int64, c_int64, _P, c_float, c_int,
                                _P, _P, c_int64, _P, _P, _P, _P, _P]),
     "som_backward_dw": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, c_int64, _P, _P, _P,
-                                c_int64, c_int64, c_int64, c_int, _P, c_int64, c_int, _P]),
+                                c_int64, c_int64, c_int64, c_int, _P, c_int64, c_int, _P, c_int64, _P]),
     "som_backward_dx": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, c_int64, _P, _P, _P,
-                                c_int64, c_int64, c_int64, c_int, _P, c_int64, c_int, _P]),
+                                c_int64, c_int64, c_int64, c_int, _P, c_int64, c_int, _P, c_int64, _P]),
     "som_debug_gemm": (c_int, [_P, _P, c_int64, c_int, _P, _P, c_int64, c_int, c_int64, c_int64, c_int64,
-                               c_int, c_int, c_int, _P, c_int64, _P]),
+                               c_int, c_int, c_int, _P, c_int64, _P, c_int64, _P]),
 }
 
 

@@ -28,7 +28,9 @@ std::atomic<int64_t> g_launches{0};
 std::atomic<int> g_bn_override{0};
 std::atomic<int> g_kchunk{16};
 std::atomic<int> g_debug{0};            // GemmShape::debug (diagnostic runs of tools/gpu_probe.py only)
-std::atomic<int> g_cg_override{0};      // 0 = cost model, 1 = single-CTA kernel, 2 = CTA-pair kernel
+std::atomic<int> g_cg_override{0};
+std::atomic<unsigned long long*> g_dbg_times{nullptr};
+std::atomic<int> g_streamk{0};          // -1 = never, 0 = cost model, 1 = whenever possible      // 0 = cost model, 1 = single-CTA kernel, 2 = CTA-pair kernel
 
 int fail(int code, const std::string& msg) {
   g_last_error = msg;
@@ -100,36 +102,53 @@ int make_tmap(CUtensorMap* map, const float* ptr, int64_t inner, int64_t outer, 
   return SOM_OK;
 }
 
-struct TileChoice { int cg; int bn; };
+struct TileChoice { int cg; int bn; int sk_workers; };
 
 // Cost model (nanoseconds) behind the tile choice, calibrated on B200 with tools/gemm_time.py:
 //  * tensor pipe: a k-block (32 deep, 12 tcgen05.mma for 3xTF32) of a 128 x bn tile per SM costs ~4.43 ns * bn at the
-//    sustained TF32 rate (822 TFLOP/s chip-wide); operands read MN-major run at ~70 % of that,
+//    sustained TF32 rate (822 TFLOP/s chip-wide),
 //  * L2 -> shared memory: each CTA pulls (128 + B rows it holds) * 256 bytes of hi+lo operands per k-block; the
 //    chip delivers ~10 TB/s in total and at most ~100 GB/s into one SM,
 //  * ~6 us per wave of tiles for prologue, epilogue and launch.
 // A CTA pair halves the B rows per SM (so 256 x 256 pair tiles are tensor-bound where 128 x 128 tiles are
-// L2-bound) but needs enough tiles to keep all 74 pairs busy; small problems prefer narrower tiles.
-TileChoice pick_tile(int64_t M, int64_t N, int64_t Kred, int sms, int a_mn, int b_mn) {
-  const int forced_bn = g_bn_override.load();
+// L2-bound) but needs enough tiles to keep all 74 pairs busy.  With a workspace the pair kernel can run stream-K:
+// the tiles' k-blocks are spread evenly over the pairs, which removes the tile-count quantisation at the price of a
+// fix-up pass over the tiles that were cut.
+TileChoice pick_tile(int64_t M, int64_t N, int64_t Kred, int sms, int b_mn, int64_t ws_floats, int bn_req) {
+  const int forced_bn = bn_req > 0 ? bn_req : g_bn_override.load();
   const int forced_cg = g_cg_override.load();
+  const int forced_sk = g_streamk.load();            // -1 = never, 0 = cost model, 1 = whenever possible
   const int64_t nkb = (Kred + som::BK - 1) / som::BK;
-  TileChoice best{1, 128};
+  TileChoice best{1, 128, 0};
   double best_cost = 1e300;
-  const double mn_penalty = (a_mn || b_mn) ? 1.4 : 1.0;
+  auto per_kb = [&](int cg, int bn, double active_sms) {
+    const double gbs_per_sm = std::min(100.0, 10000.0 / active_sms);            // GB/s == bytes/ns
+    const double t_l2 = (128.0 + static_cast<double>(bn) / cg) * 256.0 / gbs_per_sm;
+    return std::max(4.43 * bn, t_l2);
+  };
   auto consider = [&](int cg, int bn) {
     if (forced_cg && cg != forced_cg) return;
     if (forced_bn && bn != forced_bn) return;
     if (cg == 2 && b_mn && (bn / 2) % 32 != 0) return;
     const int64_t tiles = ((M + 128 * cg - 1) / (128 * cg)) * ((N + bn - 1) / bn);
     const int64_t slots = sms / cg;
-    const int64_t waves = (tiles + slots - 1) / slots;
-    const double active_sms = static_cast<double>(tiles < slots ? tiles : slots) * cg;
-    const double gbs_per_sm = std::min(100.0, 10000.0 / active_sms);            // GB/s == bytes/ns
-    const double t_l2 = (128.0 + static_cast<double>(bn) / cg) * 256.0 / gbs_per_sm;
-    const double t_mma = 4.43 * bn * mn_penalty;
-    const double cost = static_cast<double>(waves) * (static_cast<double>(nkb) * std::max(t_mma, t_l2) + 6000.0);
-    if (cost < best_cost - 1e-9) { best_cost = cost; best = TileChoice{cg, bn}; }
+    if (forced_sk <= 0 || cg == 1) {
+      const int64_t waves = (tiles + slots - 1) / slots;
+      const double active_sms = static_cast<double>(tiles < slots ? tiles : slots) * cg;
+      const double cost = static_cast<double>(waves) * (static_cast<double>(nkb) * per_kb(cg, bn, active_sms) + 6000.0);
+      if (cost < best_cost - 1e-9) { best_cost = cost; best = TileChoice{cg, bn, 0}; }
+    }
+    if (cg == 2 && forced_sk >= 0 && ws_floats > 0) {
+      const int64_t units = tiles * nkb;
+      int64_t workers = std::min<int64_t>(slots, std::max<int64_t>(1, units / 4));
+      workers = std::min<int64_t>(workers, ws_floats / (2 * 256 * static_cast<int64_t>(bn)));
+      if (workers >= 2 && tiles % workers != 0) {
+        const int64_t per_worker = (units + workers - 1) / workers;
+        const double fixup = 5000.0 + static_cast<double>(std::min<int64_t>(workers, tiles)) * 256.0 * bn * 16.0 / 3000.0;
+        const double cost = static_cast<double>(per_worker) * per_kb(2, bn, static_cast<double>(workers) * 2) + 8000.0 + fixup;
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = TileChoice{2, bn, static_cast<int>(workers)}; }
+      }
+    }
   };
   if (N <= 16 && !b_mn) consider(1, 16);
   for (int bn : {128, 96, 64, 32}) consider(1, bn);
@@ -138,6 +157,7 @@ TileChoice pick_tile(int64_t M, int64_t N, int64_t Kred, int sms, int a_mn, int 
   if (best_cost >= 1e300) {                       // overrides excluded everything: honour them literally
     best.cg = forced_cg ? forced_cg : 1;
     best.bn = forced_bn ? forced_bn : 128;
+    best.sk_workers = 0;
   }
   return best;
 }
@@ -162,20 +182,25 @@ int launch_gemm_t(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUte
     som::som_gemm3x_kernel<EPI><<<grid, som::NUM_THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, g, e);
   SOM_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
+  if (cg == 2 && g.sk_workers > 1) {
+    som::som_streamk_fixup_kernel<EPI><<<dim3(g.sk_workers - 1, 16), 256, 0, st>>>(g, e);
+    SOM_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1);
+  }
   return SOM_OK;
 }
 
 int launch_gemm(int epi, const float* a_hi, const float* a_lo, int64_t lda, int a_mn, const float* b_hi,
                 const float* b_lo, int64_t ldb, int b_mn, int64_t M, int64_t N, int64_t Kred, int bn_req,
-                int kchunk_req, int passes, const som::EpiParams& e, cudaStream_t st) {
+                int kchunk_req, int passes, const som::EpiParams& e, float* ws, int64_t ws_floats, cudaStream_t st) {
   DeviceInfo di;
   if (int rc = device_info(di)) return rc;
   if (M <= 0 || N <= 0 || Kred <= 0) return fail(SOM_ERR_ARG, "GEMM dimensions must be positive");
   if (M > (1ll << 30) || N > (1ll << 30) || Kred > (1ll << 30)) return fail(SOM_ERR_ARG, "GEMM dimension too large");
   if (!a_hi || !b_hi || (passes == 3 && (!a_lo || !b_lo))) return fail(SOM_ERR_ARG, "null GEMM operand");
   if (passes != 1 && passes != 3) return fail(SOM_ERR_ARG, "passes must be 1 or 3");
-  TileChoice tc = pick_tile(M, N, Kred, di.sms, a_mn, b_mn);
-  if (bn_req > 0) tc.bn = bn_req;
+  if (ws && (reinterpret_cast<uintptr_t>(ws) & 15) != 0) return fail(SOM_ERR_ARG, "workspace must be 16-byte aligned");
+  TileChoice tc = pick_tile(M, N, Kred, di.sms, b_mn, ws ? ws_floats : 0, bn_req);
   const int cg = tc.cg, bn = tc.bn;
   const int max_bn = cg == 2 ? som::MAX_BN_2CTA : som::MAX_BN;
   if (bn % 16 != 0 || bn < 16 || bn > max_bn) return fail(SOM_ERR_ARG, "tile width must be a multiple of 16 within the kernel's range");
@@ -188,12 +213,16 @@ int launch_gemm(int epi, const float* a_hi, const float* a_lo, int64_t lda, int 
   g.bn = bn; g.a_mn = a_mn ? 1 : 0; g.b_mn = b_mn ? 1 : 0;
   g.kchunk = kchunk_req > 0 ? kchunk_req : g_kchunk.load();
   g.passes = passes;
+  g.sk_workers = cg == 2 ? tc.sk_workers : 0;
+  g.sk_ws = ws;
   g.debug = g_debug.load();
+  g.dbg_times = g_dbg_times.load();
   g.tiles_m = static_cast<int>((M + som::BM * cg - 1) / (som::BM * cg));
   g.tiles_n = static_cast<int>((N + bn - 1) / bn);
   const size_t b_tile = g.b_mn ? static_cast<size_t>((b_rows + 31) / 32) * som::PANEL_BYTES : static_cast<size_t>(b_rows) * som::BK * 4;
   const size_t stage = 2 * som::A_TILE_BYTES + 2 * b_tile;
-  const size_t fixed = 1024 /*alignment slack*/ + 8 * (2 * som::MAX_STAGES + 4) + 16;
+  const size_t fixed = 1024 /*alignment slack*/ + som::BAR_REGION_BYTES +
+                       static_cast<size_t>(cg == 2 ? 8 : 4) * som::EPI_STG_FLOATS * sizeof(float);   // epilogue staging tiles
   int nst = static_cast<int>((som::SMEM_LIMIT - fixed) / stage);
   if (nst > som::MAX_STAGES) nst = som::MAX_STAGES;
   if (nst < 2) return fail(SOM_ERR_ARG, "tile does not fit shared memory");
@@ -209,7 +238,7 @@ int launch_gemm(int epi, const float* a_hi, const float* a_lo, int64_t lda, int 
 
   const int64_t nwork = static_cast<int64_t>(g.tiles_m) * g.tiles_n;
   const int64_t slots = di.sms / cg;
-  const int grid = static_cast<int>(nwork < slots ? nwork : slots) * cg;
+  const int grid = g.sk_workers > 0 ? g.sk_workers * cg : static_cast<int>(nwork < slots ? nwork : slots) * cg;
   switch (epi) {
     case som::EPI_RAW:  return launch_gemm_t<som::EPI_RAW>(ta_hi, ta_lo, tb_hi, tb_lo, g, e, cg, grid, smem, st);
     case som::EPI_DIST: return launch_gemm_t<som::EPI_DIST>(ta_hi, ta_lo, tb_hi, tb_lo, g, e, cg, grid, smem, st);
@@ -650,7 +679,7 @@ int launch_prep(const PrepSet& a, const PrepSet& b, int64_t dim, int mode, int64
 // ------------------------------------------------------------------------------------------------
 extern "C" {
 
-int som_b200_abi_version(void) { return 2; }
+int som_b200_abi_version(void) { return 3; }
 const char* som_last_error(void) { return g_last_error.c_str(); }
 int64_t som_launch_count(void) { return g_launches.load(); }
 void som_launch_count_reset(void) { g_launches.store(0); }
@@ -659,6 +688,9 @@ void som_set_tuning(int bn_override, int kchunk) {
   if (kchunk > 0) g_kchunk.store(kchunk);
 }
 void som_set_debug(int bits) { g_debug.store(bits); }
+void som_set_debug_times(unsigned long long* dev_buf) { g_dbg_times.store(dev_buf); }
+void som_set_streamk(int mode) { g_streamk.store(mode < 0 ? -1 : (mode > 0 ? 1 : 0)); }
+int64_t som_gemm_workspace_floats(void) { return 2ll * 74 * 256 * 256; }
 void som_set_cta_group(int cg) { g_cg_override.store(cg == 1 || cg == 2 ? cg : 0); }
 
 int som_prep_rows(const float* src, int64_t rows, int64_t dim, int64_t ld_src, int mode, float* hi, float* lo,
@@ -687,7 +719,8 @@ int som_bmu_init(long long* packed, int64_t B, void* stream) {
 
 int som_fwd_distances(const float* x_hi, const float* x_lo, int64_t ldx, const float* x_aux, const float* w_hi,
                       const float* w_lo, int64_t ldw, const float* w_aux, int64_t B, int64_t K, int64_t D, int mode,
-                      int64_t idx_offset, float* dist, int64_t ldd, long long* packed, void* stream) {
+                      int64_t idx_offset, float* dist, int64_t ldd, long long* packed, float* ws, int64_t ws_floats,
+                      void* stream) {
   if (!packed) return fail(SOM_ERR_ARG, "som_fwd_distances: packed must not be null");
   if (mode != SOM_MODE_EUCLIDEAN && mode != SOM_MODE_COSINE) return fail(SOM_ERR_ARG, "som_fwd_distances: bad mode");
   if (mode == SOM_MODE_EUCLIDEAN && (!x_aux || !w_aux)) return fail(SOM_ERR_ARG, "som_fwd_distances: norms required");
@@ -696,7 +729,8 @@ int som_fwd_distances(const float* x_hi, const float* x_lo, int64_t ldx, const f
   som::EpiParams e{};
   e.row_aux = x_aux; e.col_aux = w_aux; e.dist = dist; e.ldd = ldd; e.packed = packed;
   e.idx_offset = static_cast<int>(idx_offset); e.mode = mode;
-  return launch_gemm(som::EPI_DIST, x_hi, x_lo, ldx, 0, w_hi, w_lo, ldw, 0, B, K, D, 0, 0, 3, e, as_stream(stream));
+  return launch_gemm(som::EPI_DIST, x_hi, x_lo, ldx, 0, w_hi, w_lo, ldw, 0, B, K, D, 0, 0, 3, e, ws, ws_floats,
+                     as_stream(stream));
 }
 
 int som_bmu_decode(const long long* packed, int64_t B, int64_t K_total, int64_t* bmu, float* min_key, void* stream) {
@@ -777,22 +811,24 @@ int som_bwd_coeffs(const float* G, int64_t ldg, const float* dist, int64_t ldd, 
 
 int som_bwd_dx(const float* r_hi, const float* r_lo, int64_t ldr, const float* w_hi, const float* w_lo, int64_t ldw,
                const float* x, int64_t ldx, const float* ax, const float* bx, int64_t B, int64_t K, int64_t D,
-               float* dx, int64_t lddx, void* stream) {
+               float* dx, int64_t lddx, float* ws, int64_t ws_floats, void* stream) {
   if (!x || !ax || !bx || !dx || ldx < D || lddx < D) return fail(SOM_ERR_ARG, "som_bwd_dx: bad argument");
   som::EpiParams e{};
   e.alpha = ax; e.beta = bx; e.src = x; e.lds = ldx; e.out = dx; e.ldo = lddx;
   // C[B,D] = R[B,K] . W[K,D]: A = R K-major (reduction K contiguous), B = W MN-major (D contiguous)
-  return launch_gemm(som::EPI_GRAD, r_hi, r_lo, ldr, 0, w_hi, w_lo, ldw, 1, B, D, K, 0, 0, 3, e, as_stream(stream));
+  return launch_gemm(som::EPI_GRAD, r_hi, r_lo, ldr, 0, w_hi, w_lo, ldw, 1, B, D, K, 0, 0, 3, e, ws, ws_floats,
+                     as_stream(stream));
 }
 
 int som_bwd_dw(const float* r_hi, const float* r_lo, int64_t ldr, const float* x_hi, const float* x_lo, int64_t ldx,
                const float* w, int64_t ldw, const float* aw, const float* bw, int64_t B, int64_t K, int64_t D,
-               float* dw, int64_t lddw, void* stream) {
+               float* dw, int64_t lddw, float* ws, int64_t ws_floats, void* stream) {
   if (!w || !aw || !bw || !dw || ldw < D || lddw < D) return fail(SOM_ERR_ARG, "som_bwd_dw: bad argument");
   som::EpiParams e{};
   e.alpha = aw; e.beta = bw; e.src = w; e.lds = ldw; e.out = dw; e.ldo = lddw;
   // C[K,D] = R^T[K,B] . x[B,D]: A = R read MN-major (K contiguous), B = x MN-major (D contiguous)
-  return launch_gemm(som::EPI_GRAD, r_hi, r_lo, ldr, 1, x_hi, x_lo, ldx, 1, K, D, B, 0, 0, 3, e, as_stream(stream));
+  return launch_gemm(som::EPI_GRAD, r_hi, r_lo, ldr, 1, x_hi, x_lo, ldx, 1, K, D, B, 0, 0, 3, e, ws, ws_floats,
+                     as_stream(stream));
 }
 
 // ---- fused protocol entry points (one call per stage of the reference's call sequence) ----------------------
@@ -800,7 +836,7 @@ int som_bwd_dw(const float* r_hi, const float* r_lo, int64_t ldr, const float* x
 int som_forward(const float* x, int64_t ldx, const float* W, int64_t ldw, int64_t B, int64_t K, int64_t D, int mode,
                 int stage_w, int64_t idx_offset, float* x_hi, float* x_lo, float* x_aux, float* w_hi, float* w_lo,
                 float* w_aux, int64_t ld_stage, float* dist, int64_t ldd, long long* packed, int64_t* bmu,
-                int64_t K_total, void* stream) {
+                int64_t K_total, float* ws, int64_t ws_floats, void* stream) {
   DeviceInfo di;
   if (int rc = device_info(di)) return rc;
   if (!x || !x_hi || !x_lo || !x_aux || !w_hi || !w_lo || !w_aux || !packed)
@@ -814,7 +850,7 @@ int som_forward(const float* x, int64_t ldx, const float* W, int64_t ldw, int64_
   if (stage_w) b = PrepSet{W, K, ldw, w_hi, w_lo, w_aux, nullptr};
   if (int rc = launch_prep(a, b, D, mode, ld_stage, as_stream(stream))) return rc;
   if (int rc = som_fwd_distances(x_hi, x_lo, ld_stage, x_aux, w_hi, w_lo, ld_stage, w_aux, B, K, D, mode, idx_offset,
-                                 dist, ldd, packed, stream))
+                                 dist, ldd, packed, ws, ws_floats, stream))
     return rc;
   if (bmu) return som_bmu_decode(packed, B, K_total > 0 ? K_total : K, bmu, nullptr, stream);
   return SOM_OK;
@@ -849,35 +885,37 @@ int64_t som_loss_fused_scratch_floats(int64_t B, int64_t K) {
 int som_backward_dw(const float* r_hi, const float* r_lo, int64_t ldr, const float* x_hi, const float* x_lo,
                     int64_t ld_stage, const float* W, int64_t ldw, const float* col_sum, const float* w_aux,
                     const float* g_dev, int64_t B, int64_t K, int64_t D, int mode, float* dW, int64_t lddw,
-                    int accumulate, void* stream) {
+                    int accumulate, float* ws, int64_t ws_floats, void* stream) {
   if (!W || !col_sum || !g_dev || !dW || ldw < D || lddw < D) return fail(SOM_ERR_ARG, "som_backward_dw: bad argument");
   if (mode == SOM_MODE_COSINE && !w_aux) return fail(SOM_ERR_ARG, "som_backward_dw: cosine needs the reciprocal norms");
   som::EpiParams e{};
   e.sum = col_sum; e.aux = w_aux; e.g_dev = g_dev; e.mode = mode; e.accumulate = accumulate;
   e.src = W; e.lds = ldw; e.out = dW; e.ldo = lddw;
-  return launch_gemm(som::EPI_GRAD, r_hi, r_lo, ldr, 1, x_hi, x_lo, ld_stage, 1, K, D, B, 0, 0, 3, e, as_stream(stream));
+  return launch_gemm(som::EPI_GRAD, r_hi, r_lo, ldr, 1, x_hi, x_lo, ld_stage, 1, K, D, B, 0, 0, 3, e, ws, ws_floats,
+                     as_stream(stream));
 }
 
 int som_backward_dx(const float* r_hi, const float* r_lo, int64_t ldr, const float* w_hi, const float* w_lo,
                     int64_t ld_stage, const float* x, int64_t ldx, const float* row_sum, const float* x_aux,
                     const float* g_dev, int64_t B, int64_t K, int64_t D, int mode, float* dx, int64_t lddx,
-                    int accumulate, void* stream) {
+                    int accumulate, float* ws, int64_t ws_floats, void* stream) {
   if (!x || !row_sum || !g_dev || !dx || ldx < D || lddx < D) return fail(SOM_ERR_ARG, "som_backward_dx: bad argument");
   if (mode == SOM_MODE_COSINE && !x_aux) return fail(SOM_ERR_ARG, "som_backward_dx: cosine needs the reciprocal norms");
   som::EpiParams e{};
   e.sum = row_sum; e.aux = x_aux; e.g_dev = g_dev; e.mode = mode; e.accumulate = accumulate;
   e.src = x; e.lds = ldx; e.out = dx; e.ldo = lddx;
-  return launch_gemm(som::EPI_GRAD, r_hi, r_lo, ldr, 0, w_hi, w_lo, ld_stage, 1, B, D, K, 0, 0, 3, e, as_stream(stream));
+  return launch_gemm(som::EPI_GRAD, r_hi, r_lo, ldr, 0, w_hi, w_lo, ld_stage, 1, B, D, K, 0, 0, 3, e, ws, ws_floats,
+                     as_stream(stream));
 }
 
 int som_debug_gemm(const float* a_hi, const float* a_lo, int64_t lda, int a_mn, const float* b_hi, const float* b_lo,
                    int64_t ldb, int b_mn, int64_t M, int64_t N, int64_t Kred, int bn, int kchunk, int passes, float* C,
-                   int64_t ldc, void* stream) {
+                   int64_t ldc, float* ws, int64_t ws_floats, void* stream) {
   if (!C || ldc < N) return fail(SOM_ERR_ARG, "som_debug_gemm: bad output");
   som::EpiParams e{};
   e.out = C; e.ldo = ldc;
   return launch_gemm(som::EPI_RAW, a_hi, a_lo, lda, a_mn, b_hi, b_lo, ldb, b_mn, M, N, Kred, bn, kchunk, passes, e,
-                     as_stream(stream));
+                     ws, ws_floats, as_stream(stream));
 }
 
 }  // extern "C"

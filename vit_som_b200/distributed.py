@@ -64,9 +64,13 @@ def all_reduce_sum(t: torch.Tensor, group=None) -> torch.Tensor:
 
 
 def all_reduce_mean(t: torch.Tensor, group=None) -> torch.Tensor:
-    """DDP semantics for a replicated parameter's gradient: sum over ranks / world size."""
-    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-    t.div_(dist.get_world_size(group))
+    """DDP semantics for a replicated parameter's gradient: sum over ranks / world size.  On NCCL the division is
+    part of the collective (ReduceOp.AVG: one kernel, no extra pass over the gradient); gloo has no AVG."""
+    if t.is_cuda and dist.get_backend(group) == "nccl":
+        dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group)
+    else:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        t.div_(dist.get_world_size(group))
     return t
 
 
@@ -87,7 +91,9 @@ class DataParallelSOM:
         self.layer, self.group = layer, group
         self.world = dist.get_world_size(group)
         dev = layer.prototypes.device
-        self.comm_stream = torch.cuda.Stream(dev) if dev.type == "cuda" else None
+        # lowest priority: when dW's all-reduce and the dx GEMM become runnable together the GEMM's CTA pairs are
+        # placed first and the collective takes the SMs that are left (the GEMM never fills all 148 at these sizes)
+        self.comm_stream = torch.cuda.Stream(dev, priority=0) if dev.type == "cuda" else None
         if broadcast:
             with torch.no_grad():
                 dist.broadcast(layer.prototypes.data, src=dist.get_global_rank(group, 0) if group is not None else 0,

@@ -121,11 +121,12 @@ def forward(x: torch.Tensor, W: torch.Tensor, mode: int, ws: Staging | None = No
     packed = torch.empty((B,), device=dev, dtype=torch.int64)
     bmu = torch.empty((B,), device=dev, dtype=torch.int64) if want_bmu else None
     L = _lib.lib()
+    gws, gws_n = gemm_workspace(dev)
     if GEMM_TIMERS is None:
         check(L.som_forward(
             ptr(xf), xf.stride(0), ptr(Wf), Wf.stride(0), B, K, D, mode, 1 if stage_w else 0, idx_offset,
             xs.hi, xs.lo, xs.aux, ws.hi, ws.lo, ws.aux, xs.ld, ptr(dist_buf), ldd, ptr(packed), ptr(bmu),
-            k_total if k_total is not None else K, stream_ptr()), "som_forward")
+            k_total if k_total is not None else K, gws, gws_n, stream_ptr()), "som_forward")
     else:
         # instrumented run (bench.py roofline leg): the same launches issued one by one so that the CUDA events
         # bracket the tensor-core kernel alone
@@ -137,7 +138,7 @@ def forward(x: torch.Tensor, W: torch.Tensor, mode: int, ws: Staging | None = No
         check(L.som_bmu_init(ptr(packed), B, stream_ptr()), "som_bmu_init")
         check(_gemm("fwd", lambda: L.som_fwd_distances(xs.hi, xs.lo, xs.ld, xs.aux, ws.hi, ws.lo, ws.ld, ws.aux,
                                                        B, K, D, mode, idx_offset, ptr(dist_buf), ldd, ptr(packed),
-                                                       stream_ptr())), "som_fwd_distances")
+                                                       gws, gws_n, stream_ptr())), "som_fwd_distances")
         if bmu is not None:
             check(L.som_bmu_decode(ptr(packed), B, k_total if k_total is not None else K, ptr(bmu), None,
                                    stream_ptr()), "som_bmu_decode")
@@ -165,6 +166,17 @@ def neighbourhood(bmu: torch.Tensor, grid_pos: torch.Tensor, T_dev: torch.Tensor
 
 
 _scratch = {}
+_gemm_ws = {}
+
+
+def gemm_workspace(device):
+    """(pointer, floats) of the per-(device, stream) GEMM workspace that lets the CTA-pair kernel schedule stream-K."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    buf = _gemm_ws.get(key)
+    if buf is None:
+        buf = torch.empty((int(_lib.lib().som_gemm_workspace_floats()),), device=device, dtype=torch.float32)
+        _gemm_ws[key] = buf
+    return buf.data_ptr(), buf.numel()
 
 
 def _loss_scratch(device, n: int) -> torch.Tensor:
@@ -225,19 +237,20 @@ class FusedLossFn(torch.autograd.Function):
         dev = st.dist_buf.device
         L = _lib.lib()
         g = _grad_scalar(g_out)
+        gws, gws_n = gemm_workspace(dev)
         dx = dw = join = None
         if ctx.needs_input_grad[1]:
             dw = torch.empty((K, D), device=dev, dtype=torch.float32)
             check(_gemm("dw", lambda: L.som_backward_dw(r_hi, r_lo, ctx.ldr, st.xs.hi, st.xs.lo, st.xs.ld, ptr(st.W),
                                                         st.W.stride(0), col_sum, st.ws.aux, ptr(g), B, K, D, mode,
-                                                        ptr(dw), D, 0, stream_ptr())), "som_backward_dw")
+                                                        ptr(dw), D, 0, gws, gws_n, stream_ptr())), "som_backward_dw")
             if ctx.dw_hook is not None:
                 join = ctx.dw_hook(dw)          # data-parallel: start the prototype-gradient all-reduce now
         if ctx.needs_input_grad[0]:
             dx = torch.empty((B, D), device=dev, dtype=torch.float32)
             check(_gemm("dx", lambda: L.som_backward_dx(r_hi, r_lo, ctx.ldr, st.ws.hi, st.ws.lo, st.ws.ld, ptr(st.x),
                                                         st.x.stride(0), row_sum, st.xs.aux, ptr(g), B, K, D, mode,
-                                                        ptr(dx), D, 0, stream_ptr())), "som_backward_dx")
+                                                        ptr(dx), D, 0, gws, gws_n, stream_ptr())), "som_backward_dx")
             if dx.dtype != ctx.x_dtype:
                 dx = dx.to(ctx.x_dtype)
             dx = dx.view(ctx.x_shape)
@@ -306,11 +319,12 @@ class DistanceFn(torch.autograd.Function):
                                ptr(r_hi), ptr(r_lo), ldr, ptr(ax), ptr(bx), ptr(aw), ptr(bw), stream_ptr()),
               "som_bwd_coeffs")
         dx = dw = None
+        gws, gws_n = gemm_workspace(dev)
         if ctx.needs_input_grad[0]:
             dx = torch.empty((B, D), device=dev, dtype=torch.float32)
             check(_gemm("dx", lambda: L.som_bwd_dx(ptr(r_hi), ptr(r_lo), ldr, st.ws.hi, st.ws.lo, st.ws.ld, ptr(st.x),
                                                    st.x.stride(0), ptr(ax), ptr(bx), B, K, D, ptr(dx), D,
-                                                   stream_ptr())), "som_bwd_dx")
+                                                   gws, gws_n, stream_ptr())), "som_bwd_dx")
             if dx.dtype != ctx.x_dtype:
                 dx = dx.to(ctx.x_dtype)
             dx = dx.view(ctx.x_shape)
@@ -318,5 +332,5 @@ class DistanceFn(torch.autograd.Function):
             dw = torch.empty((K, D), device=dev, dtype=torch.float32)
             check(_gemm("dw", lambda: L.som_bwd_dw(ptr(r_hi), ptr(r_lo), ldr, st.xs.hi, st.xs.lo, st.xs.ld, ptr(st.W),
                                                    st.W.stride(0), ptr(aw), ptr(bw), B, K, D, ptr(dw), D,
-                                                   stream_ptr())), "som_bwd_dw")
+                                                   gws, gws_n, stream_ptr())), "som_bwd_dw")
         return dx, dw, None
