@@ -1,0 +1,106 @@
+"""Per-kernel timing of one SOM step through the production C-ABI entry points (run on a B200 through gpurun).
+
+    python tools/step_time.py [B K_rows K_cols D [euclidean|cosine]]
+
+Every entry point is launched `iters` times back to back behind a GPU-side sleep (so the events see GPU time
+only, L2-warm) and, for the CTA-pair GEMMs, once more with phase stamps.
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from vit_som_b200 import _lib, ops  # noqa: E402
+
+
+def timed(name, fn, iters=20, stamps=False):
+    L = _lib.lib()
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda._sleep(20_000_000)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / iters * 1e3
+    extra = ""
+    if stamps:
+        tb = torch.zeros(8, dtype=torch.int64, device="cuda")
+        L.som_set_debug_times(tb.data_ptr())
+        fn()
+        torch.cuda.synchronize()
+        L.som_set_debug_times(None)
+        t = tb.cpu().tolist()
+        names = ["setup", "prod_done", "mma_issued", "acc_ready", "epi_done", "synced", "freed"]
+        extra = "  | " + " ".join(f"{n}={(t[i + 1] - t[0]) / 1e3:.1f}" for i, n in enumerate(names) if t[i + 1])
+    print(f"{name:28s} {us:9.1f} us{extra}", flush=True)
+    return us
+
+
+def main():
+    a = sys.argv[1:]
+    B, kr, kc, D = (int(a[0]), int(a[1]), int(a[2]), int(a[3])) if len(a) >= 4 else (1024, 40, 40, 3136)
+    fcn = a[4] if len(a) > 4 else "euclidean"
+    mode = ops.MODE[fcn]
+    K = kr * kc
+    L = _lib.lib()
+    sp = _lib.stream_ptr
+    torch.manual_seed(0)
+    x = torch.randn(B, D, device="cuda")
+    W = torch.rand(K, D, device="cuda")
+    pos = torch.stack([torch.arange(kr).repeat_interleave(kc), torch.arange(kc).repeat(kr)], 1).float().cuda()
+    T = torch.full((1,), 10.0, device="cuda")
+    g = torch.ones(1, device="cuda")
+    xs, ws = ops.Staging(B, D, mode, x.device), ops.Staging(K, D, mode, x.device)
+    ldd = (K + 3) // 4 * 4
+    dist = torch.empty(B, ldd, device="cuda")
+    packed = torch.empty(B, dtype=torch.int64, device="cuda")
+    bmu = torch.empty(B, dtype=torch.int64, device="cuda")
+    rbuf = torch.empty(2 * B * ldd + B + K, device="cuda")
+    r_hi, r_lo = rbuf.data_ptr(), rbuf.data_ptr() + 4 * B * ldd
+    row_sum, col_sum = rbuf.data_ptr() + 8 * B * ldd, rbuf.data_ptr() + 8 * B * ldd + 4 * B
+    loss = torch.empty((), device="cuda")
+    scratch = torch.zeros(1 << 16, device="cuda")
+    dx, dw = torch.empty(B, D, device="cuda"), torch.empty(K, D, device="cuda")
+    gws, gws_n = ops.gemm_workspace(x.device)
+    use_ws = os.environ.get("SOM_NO_WS") is None
+    L.som_set_debug(int(os.environ.get("SOM_DEBUG", "0")))
+    wsp, wsn = (gws, gws_n) if use_ws else (None, 0)
+
+    def chk(rc, what):
+        _lib.check(rc, what)
+
+    total = 0.0
+    total += timed("prep x+W (+packed reset)", lambda: chk(L.som_forward(
+        x.data_ptr(), D, W.data_ptr(), D, B, K, D, mode, 1, 0, xs.hi, xs.lo, xs.aux, ws.hi, ws.lo, ws.aux, xs.ld,
+        None, ldd, packed.data_ptr(), None, K, wsp, wsn, sp()), "fwd") if False else chk(L.som_prep_rows(
+            x.data_ptr(), B, D, D, mode, xs.hi, xs.lo, xs.ld, xs.aux, sp()), "prep") or chk(L.som_prep_rows(
+                W.data_ptr(), K, D, D, mode, ws.hi, ws.lo, ws.ld, ws.aux, sp()), "prep"))
+    chk(L.som_bmu_init(packed.data_ptr(), B, sp()), "init")
+    total += timed("GEMM fwd (dist + argmin)", lambda: chk(L.som_fwd_distances(
+        xs.hi, xs.lo, xs.ld, xs.aux, ws.hi, ws.lo, ws.ld, ws.aux, B, K, D, mode, 0, dist.data_ptr(), ldd,
+        packed.data_ptr(), wsp, wsn, sp()), "fwd"), stamps=True)
+    timed("GEMM fwd (argmin only)", lambda: chk(L.som_fwd_distances(
+        xs.hi, xs.lo, xs.ld, xs.aux, ws.hi, ws.lo, ws.ld, ws.aux, B, K, D, mode, 0, None, ldd,
+        packed.data_ptr(), wsp, wsn, sp()), "fwd"), stamps=True)
+    total += timed("decode", lambda: chk(L.som_bmu_decode(packed.data_ptr(), B, K, bmu.data_ptr(), None, sp()), "dec"))
+    total += timed("loss + coeffs", lambda: chk(L.som_loss_fused(
+        dist.data_ptr(), ldd, bmu.data_ptr(), pos.data_ptr(), B, K, 0, T.data_ptr(), 1.0 / (B * K), mode, r_hi, r_lo,
+        ldd, row_sum, col_sum, scratch.data_ptr(), loss.data_ptr(), sp()), "loss"))
+    total += timed("GEMM dW", lambda: chk(L.som_backward_dw(
+        r_hi, r_lo, ldd, xs.hi, xs.lo, xs.ld, W.data_ptr(), D, col_sum, ws.aux, g.data_ptr(), B, K, D, mode,
+        dw.data_ptr(), D, 0, wsp, wsn, sp()), "dw"), stamps=True)
+    total += timed("GEMM dx", lambda: chk(L.som_backward_dx(
+        r_hi, r_lo, ldd, ws.hi, ws.lo, ws.ld, x.data_ptr(), D, row_sum, xs.aux, g.data_ptr(), B, K, D, mode,
+        dx.data_ptr(), D, 0, wsp, wsn, sp()), "dx"), stamps=True)
+    print(f"sum of step kernels: {total:.1f} us  (B={B} K={K} D={D} {fcn}, workspace={'yes' if use_ws else 'no'})")
+
+
+if __name__ == "__main__":
+    main()
