@@ -530,9 +530,11 @@ bwd_coeffs_kernel(const float* __restrict__ G, long long ldg, const float* __res
 //   * its row / column sums (the rank-1 coefficients of the closed-form backward).
 // The upstream gradient g_out multiplies the result in the epilogue of the gradient GEMMs, so backward needs no
 // further pass over B x K.  r_hi == nullptr: loss only (validation / no_grad).
-// Block = 16 rows x 512 columns: warp (rh, cs) owns 8 rows x 128 columns, a lane 4 consecutive columns (one
-// 16-byte load of dist, two 16-byte stores of R per row); row sums by warp shuffle, column sums in registers.
-constexpr int LC_ROWS = 16;
+// Block = 8 rows x 512 columns: warp (rh, cs) owns 4 rows x 128 columns, a lane 4 consecutive columns (one
+// 16-byte load of dist, two 16-byte stores of R per row); row sums by warp shuffle, column sums in registers, the
+// two row halves of a block combined in shared memory before the one atomicAdd per column.  The kernel is bound
+// by instruction latency (ncu: IPC 0.28 per scheduler at 14 warps/SM), hence the small blocks (27 warps/SM).
+constexpr int LC_ROWS = 8;
 constexpr int LC_COLS = 512;
 
 __global__ void __launch_bounds__(256)
@@ -545,17 +547,18 @@ loss_coeffs_kernel(const float* __restrict__ dist, long long ldd, const long lon
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rh = warp >> 2, cs = warp & 3;
   const long long k0 = static_cast<long long>(blockIdx.y) * LC_COLS + cs * 128 + lane * 4;
-  const long long b0 = static_cast<long long>(blockIdx.x) * LC_ROWS + rh * 8;
+  const long long b0 = static_cast<long long>(blockIdx.x) * LC_ROWS + rh * 4;
   const bool want_r = r_hi != nullptr;
   const bool vec = (ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(dist) & 15) == 0 &&
                    (!want_r || ((ldr & 3) == 0 && ((reinterpret_cast<uintptr_t>(r_hi) | reinterpret_cast<uintptr_t>(r_lo)) & 15) == 0));
   __shared__ float lred[8];
+  __shared__ float csum[LC_COLS];
   __shared__ double dred[256];
   __shared__ bool is_last;
 
-  // BMU grid position of this warp's 8 rows: lane r loads row r, broadcast by shuffle in the loop
+  // BMU grid position of this warp's 4 rows: lane r loads row r, broadcast by shuffle in the loop
   float2 pbv = make_float2(0.f, 0.f);
-  if (lane < 8 && b0 + lane < B) pbv = __ldg(reinterpret_cast<const float2*>(pos) + bmu[b0 + lane]);
+  if (lane < 4 && b0 + lane < B) pbv = __ldg(reinterpret_cast<const float2*>(pos) + bmu[b0 + lane]);
   const float T = __ldg(T_dev);
   const float two_t2 = 2.f * (T * T);
   float2 pk[4];
@@ -567,8 +570,8 @@ loss_coeffs_kernel(const float* __restrict__ dist, long long ldd, const long lon
   }
   float colsum[4] = {0.f, 0.f, 0.f, 0.f};
   float lsum = 0.f;
-#pragma unroll 2
-  for (int r = 0; r < 8; ++r) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
     const long long b = b0 + r;
     const float pby = __shfl_sync(0xffffffffu, pbv.x, r), pbx = __shfl_sync(0xffffffffu, pbv.y, r);
     if (b >= B) break;                                   // warp-uniform
@@ -593,7 +596,7 @@ loss_coeffs_kernel(const float* __restrict__ dist, long long ldd, const long lon
           const float g = inv_count * w;
           float rv, term;
           if (mode == 0) {
-            rv = (d[i] == 0.f) ? 0.f : g / d[i];         // ATen: ratio.masked_fill_(dist == 0, 0)
+            rv = (d[i] == 0.f) ? 0.f : __fdividef(g, d[i]);   // ATen: ratio.masked_fill_(dist == 0, 0); 2-ulp divide
             term = rv;
           } else {
             rv = g;
@@ -620,13 +623,17 @@ loss_coeffs_kernel(const float* __restrict__ dist, long long ldd, const long lon
       if (lane == 0) atomicAdd(row_sum + b, rowterm);
     }
   }
-  if (want_r) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) if (ok[i]) atomicAdd(col_sum + k0 + i, colsum[i]);
-  }
   lsum = warp_sum(lsum);
   if (lane == 0) lred[warp] = lsum;
+  if (want_r && rh == 1) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) csum[cs * 128 + lane * 4 + i] = colsum[i];
+  }
   __syncthreads();
+  if (want_r && rh == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) if (ok[i]) atomicAdd(col_sum + k0 + i, colsum[i] + csum[cs * 128 + lane * 4 + i]);
+  }
   // deterministic loss: per-block partial, last block reduces all partials in a fixed order in fp64
   const long long nblocks = static_cast<long long>(gridDim.x) * gridDim.y;
   unsigned int* counter = reinterpret_cast<unsigned int*>(partials);
