@@ -52,12 +52,18 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
-def workload_config(name, wl, world, chunk):
+def workload_config(name, wl, world, chunk, sharded=False):
     """The `config` object both arms print (same workload description, shapes and settings)."""
     desc, B, ms, D, T, fcn = wl
+    if world == 1:
+        par = "single GPU"
+    elif sharded:
+        par = f"prototype-sharded x{world}: (min,index) all-reduce, loss and dx all-reduce (one global batch)"
+    else:
+        par = f"dp{world}: batch-sharded, prototype-gradient all-reduce"
     return {"workload": f"{name}: {desc}", "B_per_gpu": B, "K": ms[0] * ms[1], "D": D, "distance": fcn, "T": T,
             "row_chunk": chunk, "l2_flush_between_steps": True,
-            "parallelism": f"dp{world}: batch-sharded, prototype-gradient all-reduce" if world > 1 else "single GPU",
+            "parallelism": par,
             "prototype_staging_in_step": True}
 
 
@@ -188,7 +194,7 @@ def run_reference_arm(args, wl):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": workload_config(args.workload, wl, args.gpus, min(B, 8192)),
+        "config": workload_config(args.workload, wl, args.gpus, min(B, 4096)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
                          "sample": f"{args.steps} full steps of {chunk} rows; {what}"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -210,6 +216,9 @@ def main():
     ap.add_argument("--distance", default=None, choices=["euclidean", "cosine"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager module calls instead of a CUDA-graph replay")
+    ap.add_argument("--shard", default="auto", choices=["auto", "batch", "prototypes"],
+                    help="multi-GPU partitioning: batch-sharded DP, or prototype-sharded (auto: prototypes for cfg5)")
+    ap.add_argument("--row-chunk", type=int, default=4096, help="rows per module call (large batches are chunked)")
     args = ap.parse_args()
     wl = list(WORKLOADS[args.workload])
     if args.distance:
@@ -233,39 +242,58 @@ def main():
     desc, B, ms, D, T, fcn = wl
     L = _lib.lib()
 
-    torch.manual_seed(1234 + rank)
-    layer = SOMLayer(make_cfg(ms, D, fcn, T)).to(dev)
+    # Partitioning over ranks: batch-sharded data parallel (weak scaling, every rank a full batch) for the ViT-SOM
+    # shapes; the 128 x 128 map of cfg5 is prototype-sharded (strong scaling: one global batch, replicated latents).
+    sharded = world > 1 and (args.shard == "prototypes" or (args.shard == "auto" and args.workload == "cfg5"))
+    chunk = min(B, args.row_chunk)             # cfg5: rows processed in chunks so the B x K scratch stays bounded
+    if sharded:
+        from vit_som_b200.distributed import PrototypeShardedSOM
+        torch.manual_seed(1234)                # identical full-map draw on every rank, each keeps its block
+        layer = PrototypeShardedSOM(make_cfg(ms, D, fcn, T)).to(dev)
+        torch.manual_seed(4321)                # replicated latents
+    else:
+        torch.manual_seed(1234 + rank)
+        layer = SOMLayer(make_cfg(ms, D, fcn, T)).to(dev)
     layer.current_temperature = T
-    chunk = min(B, 8192)                       # cfg5: rows processed in chunks so the B x K scratch stays bounded
-    x_dev = torch.randn(B, D, device=dev, requires_grad=True)
+    K_local = layer.prototypes.shape[0]
     x_host = torch.randn(B, D).pin_memory()
-    x_stage = [torch.empty(B, D, device=dev, requires_grad=True) for _ in range(2)]
+    x_full = torch.randn(B, D, device=dev)
+    # one leaf tensor per row chunk (a chunk is what one call of the module sees)
+    x_dev = [x_full[r0:r0 + chunk].clone().requires_grad_(True) for r0 in range(0, B, chunk)]
+    x_stage = [[torch.empty_like(c).requires_grad_(True) for c in x_dev] for _ in range(2)]
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
     copy_stream = torch.cuda.Stream(dev)
+    if len(x_dev) > 1:                         # chunked: the dW GEMM epilogue accumulates in place across chunks
+        layer.grad_accumulator = torch.zeros(K_local, D, device=dev)
 
     dp = None
-    if world > 1:                              # batch-sharded DP: prototype-gradient all-reduce over NVLink,
+    if world > 1 and not sharded:              # batch-sharded DP: prototype-gradient all-reduce over NVLink,
         from vit_som_b200.distributed import DataParallelSOM
         dp = DataParallelSOM(layer)            # issued on a side stream from inside backward (runs under the dx GEMM)
 
-    def hot_path(x):
-        """One step through the public module API (vit_som.py:82-86 call sequence + backward)."""
+    def hot_path(xs):
+        """One step through the public module API (vit_som.py:82-86 call sequence + backward) over all row chunks."""
         layer._w_cache = None                  # prototypes change every training step: their staging is in the step
         layer.prototypes.grad = None
-        x.grad = None
-        if chunk >= B:
+        if len(xs) == 1:
+            x = xs[0]
+            x.grad = None
             d, bmu = layer(x)
             loss = layer.som_loss(layer.compute_weights(bmu), d)
             loss.backward()
             return loss.detach()
+        layer.grad_accumulator.zero_()
         total = None
-        for r0 in range(0, B, chunk):
-            xc = x[r0:r0 + chunk]
-            d, bmu = layer(xc)
-            loss = layer.som_loss(layer.compute_weights(bmu), d) * (xc.shape[0] / B)
+        for x in xs:
+            x.grad = None
+            d, bmu = layer(x)
+            loss = layer.som_loss(layer.compute_weights(bmu), d) * (x.shape[0] / B)
             loss.backward()
             total = loss.detach() if total is None else total + loss.detach()
+        if dp is not None:                     # chunked + data parallel: one all-reduce of the accumulated gradient
+            from vit_som_b200.distributed import all_reduce_mean
+            all_reduce_mean(layer.grad_accumulator)
         return total
 
     def barrier():
@@ -353,7 +381,8 @@ def main():
     def prefetch(j):
         copy_stream.wait_event(consumed[j])            # the step that last read this buffer has finished
         with torch.cuda.stream(copy_stream), torch.no_grad():
-            x_stage[j].copy_(x_host, non_blocking=True)
+            for ci, c in enumerate(x_stage[j]):
+                c.copy_(x_host[ci * chunk:ci * chunk + c.shape[0]], non_blocking=True)
         copied[j].record(copy_stream)
 
     for j in range(2):
@@ -386,10 +415,9 @@ def main():
 
     peaks = load_peaks()
     Kp = ms[0] * ms[1]
-    flops_per_launch = 2.0 * B * Kp * D                   # algorithmic: one B x K x D contraction per GEMM launch
     n_launch = sum(len(v) for v in gemm_ms.values())
     avg_gemm_ms = sum(sum(v) for v in gemm_ms.values()) / max(n_launch, 1)
-    per_launch_flops = flops_per_launch * (chunk / B)
+    per_launch_flops = 2.0 * chunk * K_local * D          # algorithmic: one chunk x K_local x D contraction per launch
     achieved_tf = per_launch_flops / (avg_gemm_ms * 1e-3) / 1e12
     tf32_peak = peaks["bf16_tflops"] / 2.0                # tf32 dense = half the bf16 rate on the same tensor pipe
     traffic = None
@@ -408,13 +436,15 @@ def main():
         "gemm_share_of_step": sum(sum(v) for v in gemm_ms.values()) / inst_ms,
         "traffic": traffic,
     }
-    value = B * world * K_ / (total_ms * 1e-3)
-    e2e_value = B * world * K_ / (e2e_ms * 1e-3)
+    samples_per_step = B if sharded else B * world       # prototype sharding: one global batch (strong scaling)
+    value = samples_per_step * K_ / (total_ms * 1e-3)
+    e2e_value = samples_per_step * K_ / (e2e_ms * 1e-3)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K_, "warmup": W_,
-        "ms_per_step": total_ms / K_, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": total_ms / K_, "higher_is_better": True, "scaling": "strong" if sharded else "weak",
+        "vs_baseline": None,
         "dtype": "fp32 (3xTF32 tensor-core products, fp32 accumulate)", "data": "synthetic",
-        "config": dict(workload_config(args.workload, wl, world, chunk), cuda_graph=graph is not None),
+        "config": dict(workload_config(args.workload, wl, world, chunk, sharded), cuda_graph=graph is not None),
         "roofline": roofline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": 4},
         "gpu_launches": launches,

@@ -173,11 +173,15 @@ int som_forward(const float* x, int64_t ldx, const float* W, int64_t ldw,
  *   loss_out   = inv_count * sum_{b,k} w[b,k] dist[b,k]              (w recomputed in registers)
  *   R_unit     = inv_count * w / dist (0 where dist == 0) | inv_count * w (cosine), tf32 hi/lo split
  *   row_sum[b] = sum_k R_unit | sum_k R_unit (1 - dist);   col_sum[k] likewise over b
+ * grid_rows / grid_cols > 0 declare that grid_pos is the canonical square grid (cell k at (k / cols, k % cols),
+ * models/som_layer.py:61-67); the weight is then evaluated in its factorised form e[|dr|] * e[|dc|] from a small
+ * table (a few ulp from the reference's exp(-(sqrt(dr^2+dc^2))^2 / 2T^2)).  Pass 0, 0 for any other grid (hexa).
  * The upstream gradient of the loss is applied later, in the epilogue of the gradient GEMMs.
  * scratch: at least som_loss_fused_scratch_floats(B, K) floats, word 0 zero on entry (restored on exit).
  */
 int64_t som_loss_fused_scratch_floats(int64_t B, int64_t K);
 int som_loss_fused(const float* dist, int64_t ldd, const int64_t* bmu, const float* grid_pos,
+                   int grid_rows, int grid_cols,
                    int64_t B, int64_t K, int64_t k_offset, const float* T_dev, float inv_count, int mode,
                    float* r_hi, float* r_lo, int64_t ldr, float* row_sum, float* col_sum,
                    float* scratch, float* loss_out, void* stream);

@@ -69,6 +69,7 @@ def main():
     scratch = torch.zeros(1 << 16, device="cuda")
     dx, dw = torch.empty(B, D, device="cuda"), torch.empty(K, D, device="cuda")
     gws, gws_n = ops.gemm_workspace(x.device)
+    SQUARE = os.environ.get("SOM_GENERAL_GRID") is None
     use_ws = os.environ.get("SOM_NO_WS") is None
     L.som_set_debug(int(os.environ.get("SOM_DEBUG", "0")))
     wsp, wsn = (gws, gws_n) if use_ws else (None, 0)
@@ -91,7 +92,8 @@ def main():
         packed.data_ptr(), wsp, wsn, sp()), "fwd"), stamps=True)
     total += timed("decode", lambda: chk(L.som_bmu_decode(packed.data_ptr(), B, K, bmu.data_ptr(), None, sp()), "dec"))
     total += timed("loss + coeffs", lambda: chk(L.som_loss_fused(
-        dist.data_ptr(), ldd, bmu.data_ptr(), pos.data_ptr(), B, K, 0, T.data_ptr(), 1.0 / (B * K), mode, r_hi, r_lo,
+        dist.data_ptr(), ldd, bmu.data_ptr(), pos.data_ptr(), kr if SQUARE else 0, kc if SQUARE else 0, B, K, 0,
+        T.data_ptr(), 1.0 / (B * K), mode, r_hi, r_lo,
         ldd, row_sum, col_sum, scratch.data_ptr(), loss.data_ptr(), sp()), "loss"))
     total += timed("GEMM dW", lambda: chk(L.som_backward_dw(
         r_hi, r_lo, ldd, xs.hi, xs.lo, xs.ld, W.data_ptr(), D, col_sum, ws.aux, g.data_ptr(), B, K, D, mode,

@@ -109,7 +109,8 @@ struct TileChoice { int cg; int bn; int sk_workers; };
 //    sustained TF32 rate (822 TFLOP/s chip-wide),
 //  * L2 -> shared memory: each CTA pulls (128 + B rows it holds) * 256 bytes of hi+lo operands per k-block; the
 //    chip delivers ~10 TB/s in total and at most ~100 GB/s into one SM,
-//  * ~6 us per wave of tiles for prologue, epilogue and launch.
+//  * an epilogue of ~1.5 us + 0.08 us per drained column per tile, ~4 us of prologue / launch per kernel and
+//    ~12 us for the stream-K fix-up pass.
 // A CTA pair halves the B rows per SM (so 256 x 256 pair tiles are tensor-bound where 128 x 128 tiles are
 // L2-bound) but needs enough tiles to keep all 74 pairs busy.  With a workspace the pair kernel can run stream-K:
 // the tiles' k-blocks are spread evenly over the pairs, which removes the tile-count quantisation at the price of a
@@ -132,10 +133,16 @@ TileChoice pick_tile(int64_t M, int64_t N, int64_t Kred, int sms, int b_mn, int6
     if (cg == 2 && b_mn && (bn / 2) % 32 != 0) return;
     const int64_t tiles = ((M + 128 * cg - 1) / (128 * cg)) * ((N + bn - 1) / bn);
     const int64_t slots = sms / cg;
+    // epilogue of one tile: ~1.5 us + 0.08 us per column a warp drains (measured, instruction-latency bound); it hides
+    // behind the next tile's mainloop only when TMEM holds two accumulator buffers (4 * bn <= 512 columns)
+    const double t_epi = 1500.0 + 80.0 * (static_cast<double>(bn) / cg);
+    const bool overlap = 4 * bn <= som::TMEM_COLS;
     if (forced_sk <= 0 || cg == 1) {
       const int64_t waves = (tiles + slots - 1) / slots;
       const double active_sms = static_cast<double>(tiles < slots ? tiles : slots) * cg;
-      const double cost = static_cast<double>(waves) * (static_cast<double>(nkb) * per_kb(cg, bn, active_sms) + 6000.0);
+      const double t_main = static_cast<double>(nkb) * per_kb(cg, bn, active_sms);
+      const double t_tile = overlap ? std::max(t_main, t_epi) : t_main + t_epi;
+      const double cost = static_cast<double>(waves) * t_tile + (overlap ? std::min(t_main, t_epi) : 0.0) + 4000.0;
       if (cost < best_cost - 1e-9) { best_cost = cost; best = TileChoice{cg, bn, 0}; }
     }
     if (cg == 2 && forced_sk >= 0 && ws_floats > 0) {
@@ -144,8 +151,10 @@ TileChoice pick_tile(int64_t M, int64_t N, int64_t Kred, int sms, int b_mn, int6
       workers = std::min<int64_t>(workers, ws_floats / (2 * 256 * static_cast<int64_t>(bn)));
       if (workers >= 2 && tiles % workers != 0) {
         const int64_t per_worker = (units + workers - 1) / workers;
-        const double fixup = 5000.0 + static_cast<double>(std::min<int64_t>(workers, tiles)) * 256.0 * bn * 16.0 / 3000.0;
-        const double cost = static_cast<double>(per_worker) * per_kb(2, bn, static_cast<double>(workers) * 2) + 8000.0 + fixup;
+        const double segs = std::max(1.0, static_cast<double>(per_worker) / static_cast<double>(nkb)) + 1.0;
+        const double fixup = 12000.0 + static_cast<double>(std::min<int64_t>(workers, tiles)) * 256.0 * bn * 16.0 / 3000.0;
+        const double cost = static_cast<double>(per_worker) * per_kb(2, bn, static_cast<double>(workers) * 2) +
+                            segs * t_epi * (overlap ? 0.5 : 1.0) + 4000.0 + fixup;
         if (cost < best_cost - 1e-9) { best_cost = cost; best = TileChoice{2, bn, static_cast<int>(workers)}; }
       }
     }
@@ -537,90 +546,141 @@ bwd_coeffs_kernel(const float* __restrict__ G, long long ldg, const float* __res
 constexpr int LC_ROWS = 8;
 constexpr int LC_COLS = 512;
 
+// SQUARE: the map is the canonical integer grid of the square topology (models/som_layer.py:61-67), cell k at
+// (k / cols, k % cols).  Then the neighbourhood weight factorises, exp(-(dr^2 + dc^2) / 2T^2) = e[|dr|] * e[|dc|], and
+// a block needs max(rows, cols) exponentials in shared memory instead of one per element (the kernel is bound by
+// instruction issue: ~110 instructions per element on the general path, ~30 here).  The factorised weight differs
+// from the reference's exp(-(sqrt(dr^2 + dc^2))^2 / 2T^2) by a few ulp (1e-7 relative), inside the 1e-5 budget.
+constexpr int LC_MAX_TAB = 1024;
+
+template <bool SQUARE>
 __global__ void __launch_bounds__(256)
 loss_coeffs_kernel(const float* __restrict__ dist, long long ldd, const long long* __restrict__ bmu,
-                   const float* __restrict__ pos, long long B, long long K, long long k_offset,
-                   const float* __restrict__ T_dev, float inv_count, int mode,
+                   const float* __restrict__ pos, int grid_rows, int grid_cols, long long B, long long K,
+                   long long k_offset, const float* __restrict__ T_dev, float inv_count, int mode,
                    float* __restrict__ r_hi, float* __restrict__ r_lo, long long ldr,
                    float* __restrict__ row_sum, float* __restrict__ col_sum,
-                   float* __restrict__ partials, float* __restrict__ loss_out) {
+                   float* __restrict__ partials, float* __restrict__ loss_out, int rows_per_block) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rh = warp >> 2, cs = warp & 3;
+  const int half_rows = rows_per_block >> 1;              // rows handled by each of the two warp rows (multiple of 4)
   const long long k0 = static_cast<long long>(blockIdx.y) * LC_COLS + cs * 128 + lane * 4;
-  const long long b0 = static_cast<long long>(blockIdx.x) * LC_ROWS + rh * 4;
+  const long long b_base = static_cast<long long>(blockIdx.x) * rows_per_block + rh * half_rows;
   const bool want_r = r_hi != nullptr;
   const bool vec = (ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(dist) & 15) == 0 &&
                    (!want_r || ((ldr & 3) == 0 && ((reinterpret_cast<uintptr_t>(r_hi) | reinterpret_cast<uintptr_t>(r_lo)) & 15) == 0));
   __shared__ float lred[8];
   __shared__ float csum[LC_COLS];
+  __shared__ float tab[SQUARE ? LC_MAX_TAB : 1];
   __shared__ double dred[256];
   __shared__ bool is_last;
 
-  // BMU grid position of this warp's 4 rows: lane r loads row r, broadcast by shuffle in the loop
-  float2 pbv = make_float2(0.f, 0.f);
-  if (lane < 4 && b0 + lane < B) pbv = __ldg(reinterpret_cast<const float2*>(pos) + bmu[b0 + lane]);
   const float T = __ldg(T_dev);
   const float two_t2 = 2.f * (T * T);
   float2 pk[4];
+  int rk[4], ck[4];
   bool ok[4];
+  {
+    // grid cell of this lane's first column (32-bit arithmetic: K < 2^31), the next three follow by increment
+    int r0 = 0, c0 = 0;
+    if constexpr (SQUARE) {
+      const unsigned kg = static_cast<unsigned>(k_offset + k0);
+      r0 = static_cast<int>(kg / static_cast<unsigned>(grid_cols));
+      c0 = static_cast<int>(kg - static_cast<unsigned>(r0) * static_cast<unsigned>(grid_cols));
+    }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    ok[i] = k0 + i < K;
-    pk[i] = ok[i] ? __ldg(reinterpret_cast<const float2*>(pos) + k_offset + k0 + i) : make_float2(0.f, 0.f);
+    for (int i = 0; i < 4; ++i) {
+      ok[i] = k0 + i < K;
+      pk[i] = make_float2(0.f, 0.f);
+      rk[i] = r0; ck[i] = c0;
+      if constexpr (SQUARE) {
+        if (++c0 == grid_cols) { c0 = 0; ++r0; }
+      } else if (ok[i]) {
+        pk[i] = __ldg(reinterpret_cast<const float2*>(pos) + k_offset + k0 + i);
+      }
+    }
+  }
+  if constexpr (SQUARE) {
+    const int ntab = max(grid_rows, grid_cols);
+    for (int d = threadIdx.x; d < ntab; d += blockDim.x) {
+      const float fd = static_cast<float>(d);
+      tab[d] = expf(-(fd * fd) / two_t2);
+    }
+    __syncthreads();
   }
   float colsum[4] = {0.f, 0.f, 0.f, 0.f};
   float lsum = 0.f;
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const long long b = b0 + r;
-    const float pby = __shfl_sync(0xffffffffu, pbv.x, r), pbx = __shfl_sync(0xffffffffu, pbv.y, r);
-    if (b >= B) break;                                   // warp-uniform
-    float d[4] = {0.f, 0.f, 0.f, 0.f};
-    if (ok[0]) {
-      if (vec) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(dist + b * ldd + k0));
-        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  for (int r4 = 0; r4 < half_rows; r4 += 4) {
+    const long long b0 = b_base + r4;
+    if (b0 >= B) break;                                    // warp-uniform
+    // BMU grid position of the next 4 rows: lane r loads row r, broadcast by shuffle below
+    float2 pbv = make_float2(0.f, 0.f);
+    int rbv = 0, cbv = 0;
+    if (lane < 4 && b0 + lane < B) {
+      const long long bi = bmu[b0 + lane];
+      if constexpr (SQUARE) {
+        const unsigned ub = static_cast<unsigned>(bi);
+        rbv = static_cast<int>(ub / static_cast<unsigned>(grid_cols));
+        cbv = static_cast<int>(ub - static_cast<unsigned>(rbv) * static_cast<unsigned>(grid_cols));
       } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) if (ok[i]) d[i] = __ldg(dist + b * ldd + k0 + i);
+        pbv = __ldg(reinterpret_cast<const float2*>(pos) + bi);
       }
     }
-    float h[4], l[4], rowterm = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      h[i] = 0.f; l[i] = 0.f;
-      if (ok[i]) {
-        const float w = neighbourhood_weight(pk[i].x, pk[i].y, pby, pbx, two_t2);
-        lsum = fmaf(w, d[i], lsum);
-        if (want_r) {
-          const float g = inv_count * w;
-          float rv, term;
-          if (mode == 0) {
-            rv = (d[i] == 0.f) ? 0.f : __fdividef(g, d[i]);   // ATen: ratio.masked_fill_(dist == 0, 0); 2-ulp divide
-            term = rv;
-          } else {
-            rv = g;
-            term = g * (1.f - d[i]);                     // g * (x^ . w^): projection coefficient of normalize backward
-          }
-          h[i] = tf32_rna(rv);
-          l[i] = tf32_rna(rv - h[i]);
-          colsum[i] += term;
-          rowterm += term;
-        }
-      }
-    }
-    if (want_r) {
+    for (int r = 0; r < 4; ++r) {
+      const long long b = b0 + r;
+      const float pby = __shfl_sync(0xffffffffu, pbv.x, r), pbx = __shfl_sync(0xffffffffu, pbv.y, r);
+      const int rb = __shfl_sync(0xffffffffu, rbv, r), cb = __shfl_sync(0xffffffffu, cbv, r);
+      if (b >= B) break;                                   // warp-uniform
+      float d[4] = {0.f, 0.f, 0.f, 0.f};
       if (ok[0]) {
         if (vec) {
-          *reinterpret_cast<float4*>(r_hi + b * ldr + k0) = make_float4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<float4*>(r_lo + b * ldr + k0) = make_float4(l[0], l[1], l[2], l[3]);
+          const float4 v = __ldg(reinterpret_cast<const float4*>(dist + b * ldd + k0));
+          d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
         } else {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) if (ok[i]) { r_hi[b * ldr + k0 + i] = h[i]; r_lo[b * ldr + k0 + i] = l[i]; }
+          for (int i = 0; i < 4; ++i) if (ok[i]) d[i] = __ldg(dist + b * ldd + k0 + i);
         }
       }
-      rowterm = warp_sum(rowterm);
-      if (lane == 0) atomicAdd(row_sum + b, rowterm);
+      float h[4], l[4], rowterm = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        h[i] = 0.f; l[i] = 0.f;
+        if (ok[i]) {
+          float w;
+          if constexpr (SQUARE) w = tab[abs(rk[i] - rb)] * tab[abs(ck[i] - cb)];
+          else w = neighbourhood_weight(pk[i].x, pk[i].y, pby, pbx, two_t2);
+          lsum = fmaf(w, d[i], lsum);
+          if (want_r) {
+            const float g = inv_count * w;
+            float rv, term;
+            if (mode == 0) {
+              rv = (d[i] == 0.f) ? 0.f : __fdividef(g, d[i]);   // ATen: ratio.masked_fill_(dist == 0, 0); 2-ulp divide
+              term = rv;
+            } else {
+              rv = g;
+              term = g * (1.f - d[i]);                     // g * (x^ . w^): projection coefficient of normalize backward
+            }
+            h[i] = tf32_rna(rv);
+            l[i] = tf32_rna(rv - h[i]);
+            colsum[i] += term;
+            rowterm += term;
+          }
+        }
+      }
+      if (want_r) {
+        if (ok[0]) {
+          if (vec) {
+            *reinterpret_cast<float4*>(r_hi + b * ldr + k0) = make_float4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<float4*>(r_lo + b * ldr + k0) = make_float4(l[0], l[1], l[2], l[3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) if (ok[i]) { r_hi[b * ldr + k0 + i] = h[i]; r_lo[b * ldr + k0 + i] = l[i]; }
+          }
+        }
+        rowterm = warp_sum(rowterm);
+        if (lane == 0) atomicAdd(row_sum + b, rowterm);
+      }
     }
   }
   lsum = warp_sum(lsum);
@@ -664,6 +724,15 @@ loss_coeffs_kernel(const float* __restrict__ dist, long long ldd, const long lon
   }
 }
 
+// Rows per block of the fused loss kernel: as many as keep ~8 blocks per SM in flight (fewer, taller blocks amortise
+// the per-block setup and cut the column-sum atomics), between LC_ROWS and 128.
+inline int loss_rows_per_block(int64_t B, int64_t K, int sms) {
+  const int64_t col_blocks = (K + LC_COLS - 1) / LC_COLS;
+  int rpb = LC_ROWS;
+  while (rpb < 128 && ((B + 2 * rpb - 1) / (2 * rpb)) * col_blocks >= 8ll * sms) rpb *= 2;
+  return rpb;
+}
+
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 int launch_prep(const PrepSet& a, const PrepSet& b, int64_t dim, int mode, int64_t ld_out, cudaStream_t st) {
@@ -686,7 +755,7 @@ int launch_prep(const PrepSet& a, const PrepSet& b, int64_t dim, int mode, int64
 // ------------------------------------------------------------------------------------------------
 extern "C" {
 
-int som_b200_abi_version(void) { return 3; }
+int som_b200_abi_version(void) { return 4; }
 const char* som_last_error(void) { return g_last_error.c_str(); }
 int64_t som_launch_count(void) { return g_launches.load(); }
 void som_launch_count_reset(void) { g_launches.store(0); }
@@ -863,9 +932,10 @@ int som_forward(const float* x, int64_t ldx, const float* W, int64_t ldw, int64_
   return SOM_OK;
 }
 
-int som_loss_fused(const float* dist, int64_t ldd, const int64_t* bmu, const float* grid_pos, int64_t B, int64_t K,
-                   int64_t k_offset, const float* T_dev, float inv_count, int mode, float* r_hi, float* r_lo,
-                   int64_t ldr, float* row_sum, float* col_sum, float* scratch, float* loss_out, void* stream) {
+int som_loss_fused(const float* dist, int64_t ldd, const int64_t* bmu, const float* grid_pos, int grid_rows,
+                   int grid_cols, int64_t B, int64_t K, int64_t k_offset, const float* T_dev, float inv_count, int mode,
+                   float* r_hi, float* r_lo, int64_t ldr, float* row_sum, float* col_sum, float* scratch,
+                   float* loss_out, void* stream) {
   DeviceInfo di;
   if (int rc = device_info(di)) return rc;
   if (!dist || !bmu || !grid_pos || !T_dev || !scratch || !loss_out || B <= 0 || K <= 0 || ldd < K)
@@ -873,20 +943,32 @@ int som_loss_fused(const float* dist, int64_t ldd, const int64_t* bmu, const flo
   if (mode != SOM_MODE_EUCLIDEAN && mode != SOM_MODE_COSINE) return fail(SOM_ERR_ARG, "som_loss_fused: bad mode");
   if (r_hi) {
     if (!r_lo || !row_sum || !col_sum || ldr < K) return fail(SOM_ERR_ARG, "som_loss_fused: bad backward staging");
-    SOM_CUDA(cudaMemsetAsync(row_sum, 0, sizeof(float) * B, as_stream(stream)));
-    SOM_CUDA(cudaMemsetAsync(col_sum, 0, sizeof(float) * K, as_stream(stream)));
+    if (col_sum == row_sum + B) {                       // adjacent (the usual carve-up): one memset node
+      SOM_CUDA(cudaMemsetAsync(row_sum, 0, sizeof(float) * (B + K), as_stream(stream)));
+    } else {
+      SOM_CUDA(cudaMemsetAsync(row_sum, 0, sizeof(float) * B, as_stream(stream)));
+      SOM_CUDA(cudaMemsetAsync(col_sum, 0, sizeof(float) * K, as_stream(stream)));
+    }
   }
-  dim3 grid(static_cast<unsigned>((B + LC_ROWS - 1) / LC_ROWS), static_cast<unsigned>((K + LC_COLS - 1) / LC_COLS));
-  loss_coeffs_kernel<<<grid, 256, 0, as_stream(stream)>>>(dist, ldd, reinterpret_cast<const long long*>(bmu), grid_pos,
-                                                         B, K, k_offset, T_dev, inv_count, mode, r_hi, r_lo, ldr,
-                                                         row_sum, col_sum, scratch, loss_out);
+  // grid_rows / grid_cols > 0: the caller vouches that grid_pos is the canonical square grid (cell k at (k / cols, k % cols))
+  const bool square = grid_rows > 0 && grid_cols > 0 && grid_rows <= LC_MAX_TAB && grid_cols <= LC_MAX_TAB;
+  const int rpb = loss_rows_per_block(B, K, di.sms);
+  dim3 grid(static_cast<unsigned>((B + rpb - 1) / rpb), static_cast<unsigned>((K + LC_COLS - 1) / LC_COLS));
+  if (square)
+    loss_coeffs_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(
+        dist, ldd, reinterpret_cast<const long long*>(bmu), grid_pos, grid_rows, grid_cols, B, K, k_offset, T_dev,
+        inv_count, mode, r_hi, r_lo, ldr, row_sum, col_sum, scratch, loss_out, rpb);
+  else
+    loss_coeffs_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(
+        dist, ldd, reinterpret_cast<const long long*>(bmu), grid_pos, 0, 0, B, K, k_offset, T_dev,
+        inv_count, mode, r_hi, r_lo, ldr, row_sum, col_sum, scratch, loss_out, rpb);
   SOM_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
   return SOM_OK;
 }
 
 int64_t som_loss_fused_scratch_floats(int64_t B, int64_t K) {
-  return ((B + LC_ROWS - 1) / LC_ROWS) * ((K + LC_COLS - 1) / LC_COLS) + 2;
+  return ((B + LC_ROWS - 1) / LC_ROWS) * ((K + LC_COLS - 1) / LC_COLS) + 2;     // bound for any rows-per-block >= LC_ROWS
 }
 
 int som_backward_dw(const float* r_hi, const float* r_lo, int64_t ldr, const float* x_hi, const float* x_lo,

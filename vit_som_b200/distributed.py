@@ -124,8 +124,9 @@ class _ShardedLossFn(torch.autograd.Function):
     scalar all-reduce; backward = local gradient GEMMs + all-reduce of the partial dx."""
 
     @staticmethod
-    def forward(ctx, x, W, state, bmu, grid_pos, T_dev, inv_count, k_offset, want_grad, group):
-        loss = ops.FusedLossFn.forward(ctx, x, W, state, bmu, grid_pos, T_dev, inv_count, k_offset, want_grad, None)
+    def forward(ctx, x, W, state, bmu, grid_pos, T_dev, inv_count, k_offset, want_grad, group, grid_dims):
+        loss = ops.FusedLossFn.forward(ctx, x, W, state, bmu, grid_pos, T_dev, inv_count, k_offset, want_grad, None,
+                                       grid_dims)
         ctx.group = group
         return all_reduce_sum(loss, group)
 
@@ -135,7 +136,7 @@ class _ShardedLossFn(torch.autograd.Function):
         dx = grads[0]
         if dx is not None:
             all_reduce_sum(dx, ctx.group)
-        return grads + (None,) * (10 - len(grads))
+        return grads[:11]
 
 
 class PrototypeShardedSOM(SOMLayer):
@@ -179,6 +180,7 @@ class PrototypeShardedSOM(SOMLayer):
         if not want_dist:
             return None, bmu
         state.x_in, state.W_in = x, self.prototypes
+        state.grad_accum = self.grad_accumulator
         dist_local = ops.DistanceFn.apply(x, self.prototypes, state)
         dist_local._som_state = state
         return dist_local, bmu
@@ -191,4 +193,5 @@ class PrototypeShardedSOM(SOMLayer):
         B = distances.shape[0]
         want_grad = torch.is_grad_enabled() and (state.x_in.requires_grad or state.W_in.requires_grad)
         return _ShardedLossFn.apply(state.x_in, state.W_in, state, weights.bmu, self.grid_positions, weights.T_dev,
-                                    1.0 / (B * self.k_total), self.k_begin, want_grad, self.group)
+                                    1.0 / (B * self.k_total), self.k_begin, want_grad, self.group,
+                                    self._square_grid_dims())

@@ -93,7 +93,7 @@ def stage_rows(src: torch.Tensor, mode: int) -> Staging:
 class ForwardState:
     """What one forward leaves behind for the loss and the backward: raw and staged operands and the distances."""
     __slots__ = ("x", "W", "xs", "ws", "mode", "B", "K", "D", "dist_buf", "ldd", "packed", "idx_offset",
-                 "x_in", "W_in")
+                 "x_in", "W_in", "grad_accum")
 
 
 def forward(x: torch.Tensor, W: torch.Tensor, mode: int, ws: Staging | None = None, stage_w: bool = True,
@@ -145,6 +145,7 @@ def forward(x: torch.Tensor, W: torch.Tensor, mode: int, ws: Staging | None = No
     st = ForwardState()
     st.x, st.W, st.xs, st.ws, st.mode = xf, Wf, xs, ws, mode
     st.B, st.K, st.D, st.dist_buf, st.ldd, st.packed, st.idx_offset = B, K, D, dist_buf, ldd, packed, idx_offset
+    st.grad_accum = None
     return st, bmu
 
 
@@ -205,7 +206,7 @@ class FusedLossFn(torch.autograd.Function):
     (models/som_layer.py:137-152 + MeanBackward0 -> MulBackward0 -> EuclideanDistBackward0 | MmBackward0)"""
 
     @staticmethod
-    def forward(ctx, x, W, state, bmu, grid_pos, T_dev, inv_count, k_offset, want_grad, dw_hook):
+    def forward(ctx, x, W, state, bmu, grid_pos, T_dev, inv_count, k_offset, want_grad, dw_hook, grid_dims=(0, 0)):
         B, K = state.B, state.K
         dev = state.dist_buf.device
         L = _lib.lib()
@@ -219,7 +220,8 @@ class FusedLossFn(torch.autograd.Function):
             row_sum, col_sum = base + 8 * B * ldr, base + 8 * B * ldr + 4 * B
         else:
             rbuf, r_hi, r_lo, row_sum, col_sum = None, None, None, None, None
-        check(L.som_loss_fused(ptr(state.dist_buf), state.ldd, ptr(bmu), ptr(grid_pos), B, K, k_offset, ptr(T_dev),
+        check(L.som_loss_fused(ptr(state.dist_buf), state.ldd, ptr(bmu), ptr(grid_pos), int(grid_dims[0]),
+                               int(grid_dims[1]), B, K, k_offset, ptr(T_dev),
                                inv_count, state.mode, r_hi, r_lo, ldr, row_sum, col_sum, ptr(scratch), ptr(loss),
                                stream_ptr()), "som_loss_fused")
         ctx.state, ctx.rbuf, ctx.ptrs, ctx.ldr = state, rbuf, (r_hi, r_lo, row_sum, col_sum), ldr
@@ -240,11 +242,15 @@ class FusedLossFn(torch.autograd.Function):
         gws, gws_n = gemm_workspace(dev)
         dx = dw = join = None
         if ctx.needs_input_grad[1]:
-            dw = torch.empty((K, D), device=dev, dtype=torch.float32)
+            acc_buf = st.grad_accum             # row-chunked batches: the GEMM epilogue adds into this [K, D] buffer
+            dw = acc_buf if acc_buf is not None else torch.empty((K, D), device=dev, dtype=torch.float32)
             check(_gemm("dw", lambda: L.som_backward_dw(r_hi, r_lo, ctx.ldr, st.xs.hi, st.xs.lo, st.xs.ld, ptr(st.W),
                                                         st.W.stride(0), col_sum, st.ws.aux, ptr(g), B, K, D, mode,
-                                                        ptr(dw), D, 0, gws, gws_n, stream_ptr())), "som_backward_dw")
-            if ctx.dw_hook is not None:
+                                                        ptr(dw), dw.stride(0), 1 if acc_buf is not None else 0,
+                                                        gws, gws_n, stream_ptr())), "som_backward_dw")
+            if acc_buf is not None:
+                dw = None                       # already accumulated in place: nothing for autograd to add
+            elif ctx.dw_hook is not None:
                 join = ctx.dw_hook(dw)          # data-parallel: start the prototype-gradient all-reduce now
         if ctx.needs_input_grad[0]:
             dx = torch.empty((B, D), device=dev, dtype=torch.float32)
@@ -256,7 +262,7 @@ class FusedLossFn(torch.autograd.Function):
             dx = dx.view(ctx.x_shape)
         if join is not None:
             join()                              # compute stream waits for the communication stream
-        return dx, dw, None, None, None, None, None, None, None, None
+        return dx, dw, None, None, None, None, None, None, None, None, None
 
 
 class WeightedLossFn(torch.autograd.Function):

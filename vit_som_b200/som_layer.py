@@ -112,6 +112,9 @@ class SOMLayer(_Base):
         if _Base is nn.Module:
             self.trainer = None
         self._w_cache = None
+        # optional [K, D] fp32 buffer: when set, backward ADDS the prototype gradient into it from the GEMM epilogue
+        # and returns no gradient for `prototypes` to autograd (row-chunked batches accumulate without extra passes)
+        self.grad_accumulator = None
         self._dw_hook = None                                              # data-parallel wrapper: called with dW as soon as it is enqueued
 
     # ---- construction helpers -----------------------------------------------------------------
@@ -169,6 +172,7 @@ class SOMLayer(_Base):
         if not want_dist:
             return None, bmu
         state.x_in, state.W_in = x, self.prototypes
+        state.grad_accum = self.grad_accumulator
         dist = ops.DistanceFn.apply(x, self.prototypes, state)
         dist._som_state = state                          # lets som_loss take the fused path (no B x K autograd edge)
         return dist, bmu
@@ -210,6 +214,13 @@ class SOMLayer(_Base):
             raise SomError("bmu_indices must live on the GPU (no CPU path)")
         return NeighbourhoodWeights(self, bmu_indices.to(torch.int64).contiguous(), self._temperature_tensor())
 
+    def _square_grid_dims(self):
+        """(rows, cols) when grid_positions is the canonical integer grid of the square topology (then the fused loss
+        kernel evaluates the neighbourhood weight in its factorised form), else (0, 0)."""
+        if self.topology == "square":
+            return int(self.map_size[0]), int(self.map_size[1])
+        return 0, 0
+
     def som_loss(self, weights, distances):
         if isinstance(weights, NeighbourhoodWeights) and weights._dense is None:
             B, K = distances.shape
@@ -218,7 +229,8 @@ class SOMLayer(_Base):
                 # distances are this layer's own forward output: loss and its backward as one node over (x, W)
                 want_grad = torch.is_grad_enabled() and (state.x_in.requires_grad or state.W_in.requires_grad)
                 return ops.FusedLossFn.apply(state.x_in, state.W_in, state, weights.bmu, self.grid_positions,
-                                             weights.T_dev, 1.0 / (B * K), 0, want_grad, self._dw_hook)
+                                             weights.T_dev, 1.0 / (B * K), 0, want_grad, self._dw_hook,
+                                             self._square_grid_dims())
             return ops.WeightedLossFn.apply(distances, weights.bmu, self.grid_positions, weights.T_dev,
                                             1.0 / (B * K), 0)
         dense = weights.materialize() if isinstance(weights, NeighbourhoodWeights) else weights
