@@ -218,7 +218,10 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="time eager module calls instead of a CUDA-graph replay")
     ap.add_argument("--shard", default="auto", choices=["auto", "batch", "prototypes"],
                     help="multi-GPU partitioning: batch-sharded DP, or prototype-sharded (auto: prototypes for cfg5)")
-    ap.add_argument("--row-chunk", type=int, default=4096, help="rows per module call (large batches are chunked)")
+    ap.add_argument("--row-chunk", type=int, default=0,
+                    help="rows per module call (0 = 4096, times the world size when prototypes are sharded)")
+    ap.add_argument("--gemm-sms", type=int, default=-1,
+                    help="data parallel: SMs the GEMMs may occupy (0 = all, -1 = 128: ten TPCs stay free for NCCL)")
     args = ap.parse_args()
     wl = list(WORKLOADS[args.workload])
     if args.distance:
@@ -245,7 +248,8 @@ def main():
     # Partitioning over ranks: batch-sharded data parallel (weak scaling, every rank a full batch) for the ViT-SOM
     # shapes; the 128 x 128 map of cfg5 is prototype-sharded (strong scaling: one global batch, replicated latents).
     sharded = world > 1 and (args.shard == "prototypes" or (args.shard == "auto" and args.workload == "cfg5"))
-    chunk = min(B, args.row_chunk)             # cfg5: rows processed in chunks so the B x K scratch stays bounded
+    # cfg5: rows processed in chunks so the B x K_local scratch stays bounded (same bytes per chunk at any world size)
+    chunk = min(B, args.row_chunk if args.row_chunk > 0 else 4096 * (world if sharded else 1))
     if sharded:
         from vit_som_b200.distributed import PrototypeShardedSOM
         torch.manual_seed(1234)                # identical full-map draw on every rank, each keeps its block
@@ -270,7 +274,9 @@ def main():
     dp = None
     if world > 1 and not sharded:              # batch-sharded DP: prototype-gradient all-reduce over NVLink,
         from vit_som_b200.distributed import DataParallelSOM
-        dp = DataParallelSOM(layer)            # issued on a side stream from inside backward (runs under the dx GEMM)
+        # issued on a side stream from inside backward (runs under the dx GEMM, which leaves 20 SMs to NCCL)
+        gemm_sms = 128 if args.gemm_sms < 0 else args.gemm_sms
+        dp = DataParallelSOM(layer, gemm_sm_limit=gemm_sms if gemm_sms > 0 else None)
 
     def hot_path(xs):
         """One step through the public module API (vit_som.py:82-86 call sequence + backward) over all row chunks."""
@@ -408,9 +414,19 @@ def main():
         t = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, e2e_ms = t.tolist()
-    if rank != 0:
+    def finish():
+        """Leave without waiting on NCCL teardown: with collectives captured in a CUDA graph destroy_process_group has
+        been seen to block at exit; every rank synchronises, rank 0 has printed, then the process exits hard."""
         if world > 1:
-            dist.destroy_process_group()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
 
     peaks = load_peaks()
@@ -458,8 +474,7 @@ def main():
                                 "cores": torch.get_num_threads(), "kind": kind,
                                 "sample": f"{len(times)} full steps of {cchunk} rows (median); {what}"}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == "__main__":

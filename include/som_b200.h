@@ -51,6 +51,9 @@ extern "C" {
  * ws == NULL keeps the classic one-tile-per-CTA schedule.  som_gemm_workspace_floats() floats always suffice.
  */
 int64_t som_gemm_workspace_floats(void);
+/* Upper bound on the SMs the tensor-core GEMMs occupy (0 = all).  Data-parallel runs leave a few TPCs to the NCCL
+ * kernels of the prototype-gradient all-reduce so that it really runs concurrently with the dx GEMM. */
+void som_set_sm_limit(int max_sms);
 /* Stream-K policy: -1 never, 0 cost model (default), 1 whenever a workspace is available and the shape allows. */
 void som_set_streamk(int mode);
 

@@ -41,6 +41,7 @@ SIGNATURES = {
                                   c_int64, _P, c_int64, _P, _P, c_int64, _P]),
     "som_gemm_workspace_floats": (c_int64, []),
     "som_set_streamk": (None, [c_int]),
+    "som_set_sm_limit": (None, [c_int]),
     "som_bmu_decode": (c_int, [_P, c_int64, c_int64, _P, _P, _P]),
     "som_neighbourhood": (c_int, [_P, _P, c_int64, c_int64, c_int64, _P, _P, c_int64, _P]),
     "som_loss_scratch_floats": (c_int64, [c_int64, c_int64]),

@@ -30,7 +30,8 @@ std::atomic<int> g_kchunk{16};
 std::atomic<int> g_debug{0};            // GemmShape::debug (diagnostic runs of tools/gpu_probe.py only)
 std::atomic<int> g_cg_override{0};
 std::atomic<unsigned long long*> g_dbg_times{nullptr};
-std::atomic<int> g_streamk{0};          // -1 = never, 0 = cost model, 1 = whenever possible      // 0 = cost model, 1 = single-CTA kernel, 2 = CTA-pair kernel
+std::atomic<int> g_streamk{0};          // -1 = never, 0 = cost model, 1 = whenever possible
+std::atomic<int> g_sm_limit{0};         // 0 = all SMs; otherwise the GEMMs use at most this many (rest left to collectives)      // 0 = cost model, 1 = single-CTA kernel, 2 = CTA-pair kernel
 
 int fail(int code, const std::string& msg) {
   g_last_error = msg;
@@ -204,6 +205,8 @@ int launch_gemm(int epi, const float* a_hi, const float* a_lo, int64_t lda, int 
                 int kchunk_req, int passes, const som::EpiParams& e, float* ws, int64_t ws_floats, cudaStream_t st) {
   DeviceInfo di;
   if (int rc = device_info(di)) return rc;
+  const int sm_limit = g_sm_limit.load();
+  if (sm_limit >= 2 && sm_limit < di.sms) di.sms = sm_limit & ~1;      // leave SMs (whole TPC pairs) to a concurrent collective
   if (M <= 0 || N <= 0 || Kred <= 0) return fail(SOM_ERR_ARG, "GEMM dimensions must be positive");
   if (M > (1ll << 30) || N > (1ll << 30) || Kred > (1ll << 30)) return fail(SOM_ERR_ARG, "GEMM dimension too large");
   if (!a_hi || !b_hi || (passes == 3 && (!a_lo || !b_lo))) return fail(SOM_ERR_ARG, "null GEMM operand");
@@ -765,6 +768,7 @@ void som_set_tuning(int bn_override, int kchunk) {
 }
 void som_set_debug(int bits) { g_debug.store(bits); }
 void som_set_debug_times(unsigned long long* dev_buf) { g_dbg_times.store(dev_buf); }
+void som_set_sm_limit(int max_sms) { g_sm_limit.store(max_sms > 0 ? max_sms : 0); }
 void som_set_streamk(int mode) { g_streamk.store(mode < 0 ? -1 : (mode > 0 ? 1 : 0)); }
 int64_t som_gemm_workspace_floats(void) { return 2ll * 74 * 256 * 256; }
 void som_set_cta_group(int cg) { g_cg_override.store(cg == 1 || cg == 2 ? cg : 0); }

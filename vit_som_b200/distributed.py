@@ -85,10 +85,13 @@ class DataParallelSOM:
     communication stream; the dx GEMM then runs concurrently, and the compute stream joins the communication stream
     before backward returns dW to autograd.  The local loss is the mean over the local rows, as under DDP."""
 
-    def __init__(self, layer: SOMLayer, group=None, broadcast: bool = True):
+    def __init__(self, layer: SOMLayer, group=None, broadcast: bool = True, gemm_sm_limit: int | None = None):
         if not dist.is_initialized():
             raise SomError("DataParallelSOM needs an initialised torch.distributed process group")
         self.layer, self.group = layer, group
+        if gemm_sm_limit is not None and layer.prototypes.is_cuda:
+            from . import _lib
+            _lib.lib().som_set_sm_limit(int(gemm_sm_limit))   # leave TPCs free for the NCCL kernels (see som_b200.h)
         self.world = dist.get_world_size(group)
         dev = layer.prototypes.device
         # lowest priority: when dW's all-reduce and the dx GEMM become runnable together the GEMM's CTA pairs are
