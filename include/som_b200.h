@@ -47,8 +47,11 @@ extern "C" {
 /*
  * GEMM workspace.  Every entry point that launches the tensor-core GEMM takes `ws` / `ws_floats`: an optional,
  * 16-byte aligned device scratch buffer owned by the caller (one per stream in flight).  With it the CTA-pair
- * kernel may schedule stream-K (partial accumulators + a fix-up kernel) when whole tiles would leave SMs idle;
- * ws == NULL keeps the classic one-tile-per-CTA schedule.  som_gemm_workspace_floats() floats always suffice.
+ * kernel may schedule stream-K when whole tiles would leave SMs idle: pairs that hold the middle or tail of a tile
+ * leave their partial accumulators in the workspace, the pair that holds its head adds them in k order and runs the
+ * epilogue (deterministic, no extra launch).  The first 16 KiB hold the hand-over flags: zero them once after
+ * allocation (the kernel restores the zero state).  ws == NULL keeps the classic one-tile-at-a-time schedule.
+ * som_gemm_workspace_floats() floats always suffice.
  */
 int64_t som_gemm_workspace_floats(void);
 /* Upper bound on the SMs the tensor-core GEMMs occupy (0 = all).  Data-parallel runs leave a few TPCs to the NCCL
@@ -211,6 +214,19 @@ int som_backward_dx(const float* r_hi, const float* r_lo, int64_t ldr,
                     float* ws, int64_t ws_floats, void* stream);
 
 /*
+ * Both gradient GEMMs above in ONE persistent CTA-pair launch (their tiles share one stream-K work list): same
+ * results as som_backward_dw followed by som_backward_dx, one prologue / tail instead of two.  Needs the GEMM
+ * workspace; without it (or for tiny shapes) it issues the two launches.
+ */
+int som_backward_fused(const float* r_hi, const float* r_lo, int64_t ldr,
+                       const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo, int64_t ld_stage,
+                       const float* x, int64_t ldx, const float* W, int64_t ldw,
+                       const float* row_sum, const float* col_sum, const float* x_aux, const float* w_aux,
+                       const float* g_dev, int64_t B, int64_t K, int64_t D, int mode,
+                       float* dW, int64_t lddw, int accumulate_dw, float* dx, int64_t lddx,
+                       float* ws, int64_t ws_floats, void* stream);
+
+/*
  * Diagnostic entry point (used by the tests to validate the tensor-core mainloop in isolation):
  * C[M,N] = A . B^T in 3xTF32 with A = a_hi + a_lo, B = b_hi + b_lo.
  *   a_mn = 0: A stored [M, Kred] (K-major)    a_mn = 1: A stored [Kred, M] (MN-major)
@@ -229,7 +245,7 @@ void som_set_tuning(int bn_override, int kchunk);
 void som_set_cta_group(int cg);
 /* Diagnostics (results are garbage): bit 0 = no TMA loads after the first ring pass, bit 1 = no tensor-core instructions. */
 void som_set_debug(int bits);
-/* Diagnostics: device buffer of 8 uint64 in which CTA 0 of the pair kernel stamps %globaltimer (ns) at its phase
+/* Diagnostics: device buffer of 16 uint64 in which CTA 0 of the pair kernel stamps %globaltimer (ns) at its phase
  * boundaries (start, setup done, producer done, issuer done, last accumulators ready, epilogue done, pair synced,
  * TMEM freed); NULL switches it off. */
 void som_set_debug_times(unsigned long long* dev_buf);

@@ -43,8 +43,8 @@ def test_header_symbols_are_exported_and_bound(lib):
 
 
 def test_abi_version_and_pure_host_entry_points(lib):
-    assert lib.som_b200_abi_version() == 4
-    assert lib.som_gemm_workspace_floats() == 2 * 74 * 256 * 256
+    assert lib.som_b200_abi_version() == 5
+    assert lib.som_gemm_workspace_floats() == 4096 + 74 * 256 * 256
     assert lib.som_loss_scratch_floats(1024, 1600) >= 1024 * 2
     assert lib.som_loss_fused_scratch_floats(1024, 1600) == (1024 // 8) * 4 + 2
     lib.som_launch_count_reset()

@@ -251,3 +251,57 @@ def test_gradient_linearity_and_determinism(cuda_device):
     layer2 = make_layer((20, 20), 768, "euclidean", W=layer.prototypes.detach().cpu().numpy()[perm], T=5.0)
     b2 = layer2.best_matching_units(torch.as_tensor(x).cuda()).cpu().numpy()
     assert np.array_equal(perm[b2], a["bmu"])
+
+
+@pytest.mark.parametrize("shape", [(1024, (40, 40), 3136), (300, (17, 19), 520), (2048, (32, 32), 256), (129, (20, 13), 67)])
+@pytest.mark.parametrize("fcn", ["euclidean", "cosine"])
+def test_fused_backward_matches_separate_launches(shape, fcn, cuda_device):
+    """som_backward_fused (both gradient GEMMs in one stream-K launch) against som_backward_dw + som_backward_dx and
+    the fp64 oracle."""
+    from vit_som_b200 import ops
+    B, ms, D = shape
+    torch.manual_seed(11)
+    layer = make_layer(ms, D, fcn, T=3.0)
+    x = torch.randn(B, D).numpy()
+    assert ops.FUSE_BACKWARD
+    a = run_layer(layer, x, 0.7)
+    b = run_layer(layer, x, 0.7)
+    ops.FUSE_BACKWARD = False
+    try:
+        c = run_layer(layer, x, 0.7)
+    finally:
+        ops.FUSE_BACKWARD = True
+    # (row / column sums of the loss kernel are float atomics: run-to-run equal to rounding, not bitwise)
+    assert O.rel_err(a["grad_x"], b["grad_x"]) < 5e-7 and O.rel_err(a["grad_w"], b["grad_w"]) < 5e-7
+    assert O.rel_err(a["grad_x"], c["grad_x"]) < 2e-6
+    assert O.rel_err(a["grad_w"], c["grad_w"]) < 2e-6
+    W = layer.prototypes.detach().cpu().numpy()
+    r64 = O.step(x, W, O.grid_positions(ms), 3.0, fcn, 0.7, np.float64, bmu_override=a["bmu"])
+    assert O.rel_err(a["grad_x"], r64.grad_x) < GRAD_TOL
+    assert O.rel_err(a["grad_w"], r64.grad_w) < GRAD_TOL
+
+
+@pytest.mark.parametrize("fcn", ["euclidean", "cosine"])
+def test_streamk_forced_matches_oracle(fcn, cuda_device):
+    """Every CTA-pair GEMM forced onto the stream-K schedule (tiles cut across pairs, partial tiles handed over
+    through the workspace): same BMUs / loss / gradients."""
+    from vit_som_b200 import _lib
+    B, ms, D, T = 1024, (24, 24), 1000, 6.0
+    torch.manual_seed(5)
+    layer = make_layer(ms, D, fcn, T=T)
+    x = torch.randn(B, D).numpy()
+    W = layer.prototypes.detach().cpu().numpy()
+    pos = O.grid_positions(ms)
+    L = _lib.lib()
+    L.som_set_streamk(1)
+    L.som_set_cta_group(2)
+    try:
+        out = run_layer(layer, x)
+        again = run_layer(layer, x)
+    finally:
+        L.som_set_streamk(0)
+        L.som_set_cta_group(0)
+    ref = O.step(x, W, pos, T, fcn, 1.0, np.float32)
+    check_against(out, ref.distances, ref.bmu, float(ref.loss), ref.grad_x, ref.grad_w, x, W, fcn, pos, T, 1.0)
+    assert out["loss"] == again["loss"] and np.array_equal(out["distances"], again["distances"])
+    assert O.rel_err(out["grad_w"], again["grad_w"]) < 5e-7

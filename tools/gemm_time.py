@@ -24,7 +24,7 @@ def main():
         fields = [int(t) for t in spec.split(",")]
         M, N, K, a_mn, b_mn, cg, bn, kchunk, debug = fields[:9]
         sk = fields[9] if len(fields) > 9 else -1
-        WS = torch.empty(int(L.som_gemm_workspace_floats()), device="cuda") if sk >= 0 else None
+        WS = torch.zeros(int(L.som_gemm_workspace_floats()), device="cuda") if sk >= 0 else None
         L.som_set_streamk(sk)
         torch.manual_seed(0)
         lda = (M if a_mn else K)

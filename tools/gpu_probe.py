@@ -28,7 +28,7 @@ def _setup_streamk(L):
         return
     L.som_set_streamk(int(mode))
     if WS is None and int(mode) >= 0:
-        WS = torch.empty(int(L.som_gemm_workspace_floats()), device="cuda")
+        WS = torch.zeros(int(L.som_gemm_workspace_floats()), device="cuda")
 
 
 def split_tf32(x):

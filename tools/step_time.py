@@ -31,14 +31,17 @@ def timed(name, fn, iters=20, stamps=False):
     us = e0.elapsed_time(e1) / iters * 1e3
     extra = ""
     if stamps:
-        tb = torch.zeros(8, dtype=torch.int64, device="cuda")
+        tb = torch.zeros(16, dtype=torch.int64, device="cuda")
         L.som_set_debug_times(tb.data_ptr())
         fn()
         torch.cuda.synchronize()
         L.som_set_debug_times(None)
         t = tb.cpu().tolist()
-        names = ["setup", "prod_done", "mma_issued", "acc_ready", "epi_done", "synced", "freed"]
+        names = ["setup", "prod_done", "mma_issued", "acc_ready", "epi_done", "synced", "freed", "acc_in_regs", "pre_epi"]
         extra = "  | " + " ".join(f"{n}={(t[i + 1] - t[0]) / 1e3:.1f}" for i, n in enumerate(names) if t[i + 1])
+        if t[13]:     # epilogue cycle counters of warp 4 / CTA 0 (1.965 GHz): TMEM load, math, store per 16-column block
+            extra += (f" || epi blocks={t[13]} ld={t[10] / 1965 / t[13]:.2f} math={t[11] / 1965 / t[13]:.2f} "
+                      f"st={t[12] / 1965 / t[13]:.2f} us/block; sk wait={t[14] / 1965:.1f} add={t[15] / 1965:.1f} us")
     print(f"{name:28s} {us:9.1f} us{extra}", flush=True)
     return us
 
@@ -101,6 +104,10 @@ def main():
     total += timed("GEMM dx", lambda: chk(L.som_backward_dx(
         r_hi, r_lo, ldd, ws.hi, ws.lo, ws.ld, x.data_ptr(), D, row_sum, xs.aux, g.data_ptr(), B, K, D, mode,
         dx.data_ptr(), D, 0, wsp, wsn, sp()), "dx"), stamps=True)
+    timed("GEMM dW+dx fused launch", lambda: chk(L.som_backward_fused(
+        r_hi, r_lo, ldd, xs.hi, xs.lo, ws.hi, ws.lo, xs.ld, x.data_ptr(), D, W.data_ptr(), D, row_sum, col_sum,
+        xs.aux, ws.aux, g.data_ptr(), B, K, D, mode, dw.data_ptr(), D, 0, dx.data_ptr(), D, wsp, wsn, sp()), "bwd"),
+        stamps=True)
     print(f"sum of step kernels: {total:.1f} us  (B={B} K={K} D={D} {fcn}, workspace={'yes' if use_ws else 'no'})")
 
 

@@ -62,6 +62,9 @@ SIGNATURES = {
                                 c_int64, c_int64, c_int64, c_int, _P, c_int64, c_int, _P, c_int64, _P]),
     "som_backward_dx": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, c_int64, _P, _P, _P,
                                 c_int64, c_int64, c_int64, c_int, _P, c_int64, c_int, _P, c_int64, _P]),
+    "som_backward_fused": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, c_int64, _P, c_int64, _P, c_int64, _P, _P, _P, _P,
+                                   _P, c_int64, c_int64, c_int64, c_int, _P, c_int64, c_int, _P, c_int64,
+                                   _P, c_int64, _P]),
     "som_debug_gemm": (c_int, [_P, _P, c_int64, c_int, _P, _P, c_int64, c_int, c_int64, c_int64, c_int64,
                                c_int, c_int, c_int, _P, c_int64, _P, c_int64, _P]),
 }

@@ -103,7 +103,9 @@ int make_tmap(CUtensorMap* map, const float* ptr, int64_t inner, int64_t outer, 
   return SOM_OK;
 }
 
-struct TileChoice { int cg; int bn; int sk_workers; };
+struct TileChoice { int cg; int bn; int sk_workers; int sk_split; };
+
+constexpr int64_t SK_FLAG_WORDS = 4096;      // head of the GEMM workspace: stream-K flags, [worker][16] (<= 256 workers)
 
 // Cost model (nanoseconds) behind the tile choice, calibrated on B200 with tools/gemm_time.py:
 //  * tensor pipe: a k-block (32 deep, 12 tcgen05.mma for 3xTF32) of a 128 x bn tile per SM costs ~4.43 ns * bn at the
@@ -111,23 +113,40 @@ struct TileChoice { int cg; int bn; int sk_workers; };
 //  * L2 -> shared memory: each CTA pulls (128 + B rows it holds) * 256 bytes of hi+lo operands per k-block; the
 //    chip delivers ~10 TB/s in total and at most ~100 GB/s into one SM,
 //  * an epilogue of ~1.5 us + 0.08 us per drained column per tile, ~4 us of prologue / launch per kernel and
-//    ~12 us for the stream-K fix-up pass.
+//    ~3 us for the exchange of stream-K partial tiles through L2.
 // A CTA pair halves the B rows per SM (so 256 x 256 pair tiles are tensor-bound where 128 x 128 tiles are
 // L2-bound) but needs enough tiles to keep all 74 pairs busy.  With a workspace the pair kernel can run stream-K:
-// the tiles' k-blocks are spread evenly over the pairs, which removes the tile-count quantisation at the price of a
-// fix-up pass over the tiles that were cut.
+// the tiles' k-blocks are spread evenly over the pairs, which removes the tile-count quantisation at the price of
+// one partial-tile round trip through L2 per pair.
+double per_kb_ns(int cg, int bn, double active_sms) {
+  const double gbs_per_sm = std::min(100.0, 10000.0 / active_sms);            // GB/s == bytes/ns
+  const double t_l2 = (128.0 + static_cast<double>(bn) / cg) * 256.0 / gbs_per_sm;
+  return std::max(4.43 * bn, t_l2);
+}
+// Stream-K workers for `units` k-block units of 256 x bn pair tiles (0 = do not use stream-K).
+int64_t streamk_workers(int64_t units, int64_t slots, int bn, int64_t ws_floats) {
+  int64_t workers = std::min<int64_t>(slots, std::max<int64_t>(1, units / 4));
+  workers = std::min<int64_t>(workers, (ws_floats - SK_FLAG_WORDS) / (256 * static_cast<int64_t>(bn)));
+  workers = std::min<int64_t>(workers, SK_FLAG_WORDS / 16);
+  return workers >= 2 ? workers : 0;
+}
+double streamk_cost_ns(int64_t units, int64_t workers, int64_t nkb_typ, int bn) {
+  const int64_t per_worker = (units + workers - 1) / workers;
+  const double t_epi = 1500.0 + 80.0 * (static_cast<double>(bn) / 2);
+  // the pair kernel always has two TMEM buffers: only the last drain of a worker is exposed, the others cost a
+  // stall of the issuer when they outlast an accumulation chunk (charged at a quarter)
+  const double segs = std::max(1.0, static_cast<double>(per_worker) / static_cast<double>(nkb_typ)) + 1.0;
+  return static_cast<double>(per_worker) * per_kb_ns(2, bn, static_cast<double>(workers) * 2) +
+         t_epi + (segs - 1.0) * t_epi * 0.25 + 4000.0 + 2000.0;
+}
+
 TileChoice pick_tile(int64_t M, int64_t N, int64_t Kred, int sms, int b_mn, int64_t ws_floats, int bn_req) {
   const int forced_bn = bn_req > 0 ? bn_req : g_bn_override.load();
   const int forced_cg = g_cg_override.load();
   const int forced_sk = g_streamk.load();            // -1 = never, 0 = cost model, 1 = whenever possible
   const int64_t nkb = (Kred + som::BK - 1) / som::BK;
-  TileChoice best{1, 128, 0};
+  TileChoice best{1, 128, 0, 0};
   double best_cost = 1e300;
-  auto per_kb = [&](int cg, int bn, double active_sms) {
-    const double gbs_per_sm = std::min(100.0, 10000.0 / active_sms);            // GB/s == bytes/ns
-    const double t_l2 = (128.0 + static_cast<double>(bn) / cg) * 256.0 / gbs_per_sm;
-    return std::max(4.43 * bn, t_l2);
-  };
   auto consider = [&](int cg, int bn) {
     if (forced_cg && cg != forced_cg) return;
     if (forced_bn && bn != forced_bn) return;
@@ -135,28 +154,36 @@ TileChoice pick_tile(int64_t M, int64_t N, int64_t Kred, int sms, int b_mn, int6
     const int64_t tiles = ((M + 128 * cg - 1) / (128 * cg)) * ((N + bn - 1) / bn);
     const int64_t slots = sms / cg;
     // epilogue of one tile: ~1.5 us + 0.08 us per column a warp drains (measured, instruction-latency bound); it hides
-    // behind the next tile's mainloop only when TMEM holds two accumulator buffers (4 * bn <= 512 columns)
+    // behind the next tile's mainloop only when TMEM holds two accumulator buffers (the pair kernel always does,
+    // the single-CTA kernel when 4 * bn <= 512 columns)
     const double t_epi = 1500.0 + 80.0 * (static_cast<double>(bn) / cg);
-    const bool overlap = 4 * bn <= som::TMEM_COLS;
+    const bool overlap = cg == 2 || 4 * bn <= som::TMEM_COLS;
     if (forced_sk <= 0 || cg == 1) {
       const int64_t waves = (tiles + slots - 1) / slots;
       const double active_sms = static_cast<double>(tiles < slots ? tiles : slots) * cg;
-      const double t_main = static_cast<double>(nkb) * per_kb(cg, bn, active_sms);
+      const double t_main = static_cast<double>(nkb) * per_kb_ns(cg, bn, active_sms);
       const double t_tile = overlap ? std::max(t_main, t_epi) : t_main + t_epi;
       const double cost = static_cast<double>(waves) * t_tile + (overlap ? std::min(t_main, t_epi) : 0.0) + 4000.0;
-      if (cost < best_cost - 1e-9) { best_cost = cost; best = TileChoice{cg, bn, 0}; }
+      if (cost < best_cost - 1e-9) { best_cost = cost; best = TileChoice{cg, bn, 0, 0}; }
     }
     if (cg == 2 && forced_sk >= 0 && ws_floats > 0) {
       const int64_t units = tiles * nkb;
-      int64_t workers = std::min<int64_t>(slots, std::max<int64_t>(1, units / 4));
-      workers = std::min<int64_t>(workers, ws_floats / (2 * 256 * static_cast<int64_t>(bn)));
+      const int64_t workers = streamk_workers(units, slots, bn, ws_floats);
       if (workers >= 2 && tiles % workers != 0) {
-        const int64_t per_worker = (units + workers - 1) / workers;
-        const double segs = std::max(1.0, static_cast<double>(per_worker) / static_cast<double>(nkb)) + 1.0;
-        const double fixup = 12000.0 + static_cast<double>(std::min<int64_t>(workers, tiles)) * 256.0 * bn * 16.0 / 3000.0;
-        const double cost = static_cast<double>(per_worker) * per_kb(2, bn, static_cast<double>(workers) * 2) +
-                            segs * t_epi * (overlap ? 0.5 : 1.0) + 4000.0 + fixup;
-        if (cost < best_cost - 1e-9) { best_cost = cost; best = TileChoice{2, bn, static_cast<int>(workers)}; }
+        const double cost = streamk_cost_ns(units, workers, nkb, bn);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = TileChoice{2, bn, static_cast<int>(workers), 0}; }
+      }
+      // tile-aligned split-K: fewer tiles than pairs -> every tile cut into `split` equal pieces, one partial-tile
+      // hand-over per piece and no slivers (preferred over even ranges at equal cost: it exchanges less)
+      const int64_t split = tiles > 0 ? std::min<int64_t>(slots / tiles, nkb / 8) : 0;
+      if (split >= 2 && tiles * split <= workers) {
+        const int64_t piece = (nkb + split - 1) / split;
+        const double cost = static_cast<double>(piece) * per_kb_ns(2, bn, static_cast<double>(tiles * split) * 2) +
+                            t_epi + 4000.0 + 2000.0;
+        if (cost < best_cost * 1.02) {
+          best_cost = std::min(best_cost, cost);
+          best = TileChoice{2, bn, static_cast<int>(tiles * split), static_cast<int>(split)};
+        }
       }
     }
   };
@@ -168,93 +195,180 @@ TileChoice pick_tile(int64_t M, int64_t N, int64_t Kred, int sms, int b_mn, int6
     best.cg = forced_cg ? forced_cg : 1;
     best.bn = forced_bn ? forced_bn : 128;
     best.sk_workers = 0;
+    best.sk_split = 0;
   }
   return best;
 }
 
+// One GEMM as its caller states it: C[M,N] = A . B^T with the epilogue `epi` / `e`.
+struct Problem {
+  const float* a_hi; const float* a_lo; int64_t lda; int a_mn;
+  const float* b_hi; const float* b_lo; int64_t ldb; int b_mn;
+  int64_t M, N, Kred;
+  som::EpiParams e;
+};
+
+int check_problem(const Problem& p, int passes) {
+  if (p.M <= 0 || p.N <= 0 || p.Kred <= 0) return fail(SOM_ERR_ARG, "GEMM dimensions must be positive");
+  if (p.M > (1ll << 30) || p.N > (1ll << 30) || p.Kred > (1ll << 30)) return fail(SOM_ERR_ARG, "GEMM dimension too large");
+  if (!p.a_hi || !p.b_hi || (passes == 3 && (!p.a_lo || !p.b_lo))) return fail(SOM_ERR_ARG, "null GEMM operand");
+  return SOM_OK;
+}
+
+// Tensor maps of one problem: A boxes of `a_rows` rows, B boxes of `b_rows` rows (K-major) or 32 x 32 panels (MN-major).
+int make_problem_maps(const Problem& p, int a_rows, int b_rows, CUtensorMap* a_hi, CUtensorMap* a_lo, CUtensorMap* b_hi,
+                      CUtensorMap* b_lo) {
+  int rc;
+  const float* alo = p.a_lo ? p.a_lo : p.a_hi;
+  const float* blo = p.b_lo ? p.b_lo : p.b_hi;
+  if (p.a_mn) { if ((rc = make_tmap(a_hi, p.a_hi, p.M, p.Kred, p.lda, 32, true))) return rc; if ((rc = make_tmap(a_lo, alo, p.M, p.Kred, p.lda, 32, true))) return rc; }
+  else        { if ((rc = make_tmap(a_hi, p.a_hi, p.Kred, p.M, p.lda, a_rows))) return rc; if ((rc = make_tmap(a_lo, alo, p.Kred, p.M, p.lda, a_rows))) return rc; }
+  if (p.b_mn) { if ((rc = make_tmap(b_hi, p.b_hi, p.N, p.Kred, p.ldb, 32, true))) return rc; if ((rc = make_tmap(b_lo, blo, p.N, p.Kred, p.ldb, 32, true))) return rc; }
+  else        { if ((rc = make_tmap(b_hi, p.b_hi, p.Kred, p.N, p.ldb, b_rows))) return rc; if ((rc = make_tmap(b_lo, blo, p.Kred, p.N, p.ldb, b_rows))) return rc; }
+  return SOM_OK;
+}
+
+void fill_shape(som::GemmShape& g, const Problem& p, int cg, int bn, int kchunk, int passes) {
+  g = som::GemmShape{};
+  g.M = static_cast<int>(p.M); g.N = static_cast<int>(p.N); g.Kred = static_cast<int>(p.Kred);
+  g.bn = bn; g.a_mn = p.a_mn ? 1 : 0; g.b_mn = p.b_mn ? 1 : 0;
+  g.kchunk = kchunk; g.passes = passes; g.nprob = 1;
+  g.debug = g_debug.load();
+  g.dbg_times = g_dbg_times.load();
+  g.tiles_m = static_cast<int>((p.M + som::BM * cg - 1) / (som::BM * cg));
+  g.tiles_n = static_cast<int>((p.N + bn - 1) / bn);
+}
+
 template <int EPI>
-int launch_gemm_t(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi,
-                  const CUtensorMap& tb_lo, const som::GemmShape& g, const som::EpiParams& e, int cg, int grid,
-                  size_t smem, cudaStream_t st) {
-  static bool attr_set[3] = {false, false, false};
-  if (!attr_set[cg]) {
-    if (cg == 2)
-      SOM_CUDA(cudaFuncSetAttribute(som::som_gemm3x_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    som::SMEM_LIMIT));
-    else
-      SOM_CUDA(cudaFuncSetAttribute(som::som_gemm3x_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    som::SMEM_LIMIT));
-    attr_set[cg] = true;
+int launch_single_t(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi,
+                    const CUtensorMap& tb_lo, const som::GemmShape& g, const som::EpiParams& e, int grid, size_t smem,
+                    cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SOM_CUDA(cudaFuncSetAttribute(som::som_gemm3x_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  som::SMEM_LIMIT));
+    attr_set = true;
   }
-  if (cg == 2)
-    som::som_gemm3x_pair_kernel<EPI><<<grid, som::NUM_THREADS_2CTA, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, g, e);
-  else
-    som::som_gemm3x_kernel<EPI><<<grid, som::NUM_THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, g, e);
+  som::som_gemm3x_kernel<EPI><<<grid, som::NUM_THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, g, e);
   SOM_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
-  if (cg == 2 && g.sk_workers > 1) {
-    som::som_streamk_fixup_kernel<EPI><<<dim3(g.sk_workers - 1, 16), 256, 0, st>>>(g, e);
-    SOM_CUDA(cudaGetLastError());
-    g_launches.fetch_add(1);
+  return SOM_OK;
+}
+
+template <int EPI>
+int launch_pair_t(const som::PairMaps& m0, const som::PairMaps& m1, const som::GemmShape& g0, const som::EpiParams& e0,
+                  const som::GemmShape& g1, const som::EpiParams& e1, int grid, size_t smem, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SOM_CUDA(cudaFuncSetAttribute(som::som_gemm3x_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  som::SMEM_LIMIT));
+    attr_set = true;
   }
+  som::som_gemm3x_pair_kernel<EPI><<<grid, som::NUM_THREADS_2CTA, smem, st>>>(m0, m1, g0, e0, g1, e1);
+  SOM_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return SOM_OK;
+}
+
+std::atomic<unsigned int> g_sk_token{0};
+
+// The pair kernel adds all three 3xTF32 products into one accumulator, i.e. three tensor-core roundings per k-step
+// where the two-accumulator kernel has one on its main chain.  Half the k-blocks per chain (8 instead of 16) keeps
+// the rounding bias of an all-positive reduction at ~2e-6 relative (measured; budget 1e-5) while a chunk still
+// lasts long enough (~7 us) for the epilogue warps to finish a tile epilogue under it.
+int pair_kchunk(int kchunk, int passes) { return passes == 3 ? std::max(1, kchunk / 2) : kchunk; }
+
+// CTA-pair launch of one or two GEMMs that share the tile width, the accumulation chunking and the epilogue kind.
+int launch_pair(int epi, const Problem* probs, int nprob, int bn, int sk_workers, int sk_split, int kchunk, int passes,
+                float* ws, int sms, cudaStream_t st) {
+  if (bn % 32 != 0 || bn < 32 || bn > som::MAX_BN_2CTA)
+    return fail(SOM_ERR_ARG, "pair tile width must be a multiple of 32 within the kernel's range");
+  const int b_rows = bn / 2;                       // rows of the B tile held by one CTA
+  bool need64 = nprob > 1;
+  for (int i = 0; i < nprob; ++i) need64 = need64 || probs[i].b_mn;
+  if (need64 && b_rows % 32 != 0) return fail(SOM_ERR_ARG, "pair tile width must be a multiple of 64 for MN-major B");
+  som::PairMaps maps[2];
+  som::GemmShape g[2];
+  int64_t nwork = 0;
+  for (int i = 0; i < nprob; ++i) {
+    if (int rc = check_problem(probs[i], passes)) return rc;
+    if (int rc = make_problem_maps(probs[i], som::BM, b_rows, &maps[i].a_hi, &maps[i].a_lo, &maps[i].b_hi, &maps[i].b_lo))
+      return rc;
+    fill_shape(g[i], probs[i], 2, bn, kchunk, passes);
+    nwork += static_cast<int64_t>(g[i].tiles_m) * g[i].tiles_n;
+  }
+  if (nprob == 1) { maps[1] = maps[0]; g[1] = g[0]; }
+  const size_t b_tile = static_cast<size_t>(b_rows) * som::BK * 4;
+  const size_t stage = 2 * som::A_TILE_BYTES + 2 * b_tile;
+  const size_t fixed = 1024 /*alignment slack*/ + som::BAR_REGION_BYTES;
+  int nst = static_cast<int>((som::SMEM_LIMIT - fixed) / stage);
+  if (nst > som::MAX_STAGES) nst = som::MAX_STAGES;
+  if (nst < 2) return fail(SOM_ERR_ARG, "tile does not fit shared memory");
+  g[0].nstages = nst;
+  g[0].nprob = nprob;
+  g[0].sk_workers = ws ? sk_workers : 0;
+  g[0].sk_split = g[0].sk_workers > 0 ? sk_split : 0;
+  if (g[0].sk_workers > 0) {
+    g[0].sk_flags = reinterpret_cast<unsigned int*>(ws);
+    g[0].sk_ws = ws + SK_FLAG_WORDS;
+    g[0].sk_token = 0x80000000u | (g_sk_token.fetch_add(1) + 1u);
+  }
+  const size_t smem = fixed + nst * stage;
+  const int64_t slots = sms / 2;
+  const int grid = g[0].sk_workers > 0 ? g[0].sk_workers * 2 : static_cast<int>(nwork < slots ? nwork : slots) * 2;
+  som::EpiParams e0 = probs[0].e, e1 = probs[nprob - 1].e;
+  e0.dbg = e1.dbg = g_debug.load();
+  switch (epi) {
+    case som::EPI_RAW:  return launch_pair_t<som::EPI_RAW>(maps[0], maps[1], g[0], e0, g[1], e1, grid, smem, st);
+    case som::EPI_DIST: return launch_pair_t<som::EPI_DIST>(maps[0], maps[1], g[0], e0, g[1], e1, grid, smem, st);
+    case som::EPI_GRAD: return launch_pair_t<som::EPI_GRAD>(maps[0], maps[1], g[0], e0, g[1], e1, grid, smem, st);
+  }
+  return fail(SOM_ERR_ARG, "unknown epilogue");
+}
+
+int effective_sms(int* sms) {
+  DeviceInfo di;
+  if (int rc = device_info(di)) return rc;
+  const int sm_limit = g_sm_limit.load();
+  if (sm_limit >= 2 && sm_limit < di.sms) di.sms = sm_limit & ~1;      // leave SMs (whole TPC pairs) to a concurrent collective
+  *sms = di.sms;
   return SOM_OK;
 }
 
 int launch_gemm(int epi, const float* a_hi, const float* a_lo, int64_t lda, int a_mn, const float* b_hi,
                 const float* b_lo, int64_t ldb, int b_mn, int64_t M, int64_t N, int64_t Kred, int bn_req,
                 int kchunk_req, int passes, const som::EpiParams& e, float* ws, int64_t ws_floats, cudaStream_t st) {
-  DeviceInfo di;
-  if (int rc = device_info(di)) return rc;
-  const int sm_limit = g_sm_limit.load();
-  if (sm_limit >= 2 && sm_limit < di.sms) di.sms = sm_limit & ~1;      // leave SMs (whole TPC pairs) to a concurrent collective
-  if (M <= 0 || N <= 0 || Kred <= 0) return fail(SOM_ERR_ARG, "GEMM dimensions must be positive");
-  if (M > (1ll << 30) || N > (1ll << 30) || Kred > (1ll << 30)) return fail(SOM_ERR_ARG, "GEMM dimension too large");
-  if (!a_hi || !b_hi || (passes == 3 && (!a_lo || !b_lo))) return fail(SOM_ERR_ARG, "null GEMM operand");
+  int sms = 0;
+  if (int rc = effective_sms(&sms)) return rc;
   if (passes != 1 && passes != 3) return fail(SOM_ERR_ARG, "passes must be 1 or 3");
   if (ws && (reinterpret_cast<uintptr_t>(ws) & 15) != 0) return fail(SOM_ERR_ARG, "workspace must be 16-byte aligned");
-  TileChoice tc = pick_tile(M, N, Kred, di.sms, b_mn, ws ? ws_floats : 0, bn_req);
+  Problem p{a_hi, a_lo, lda, a_mn, b_hi, b_lo, ldb, b_mn, M, N, Kred, e};
+  if (int rc = check_problem(p, passes)) return rc;
+  TileChoice tc = pick_tile(M, N, Kred, sms, b_mn, ws ? ws_floats : 0, bn_req);
   const int cg = tc.cg, bn = tc.bn;
-  const int max_bn = cg == 2 ? som::MAX_BN_2CTA : som::MAX_BN;
-  if (bn % 16 != 0 || bn < 16 || bn > max_bn) return fail(SOM_ERR_ARG, "tile width must be a multiple of 16 within the kernel's range");
-  if (cg == 2 && (bn % 32 != 0 || (b_mn && (bn / 2) % 32 != 0)))
-    return fail(SOM_ERR_ARG, "pair tile width must be a multiple of 32 (64 for MN-major B)");
-  const int b_rows = bn / cg;                     // rows of the B tile held by one CTA
+  const int kchunk = kchunk_req > 0 ? kchunk_req : g_kchunk.load();
+  if (cg == 2)
+    return launch_pair(epi, &p, 1, bn, tc.sk_workers, tc.sk_split, pair_kchunk(kchunk, passes), passes, ws, sms, st);
 
+  if (bn % 16 != 0 || bn < 16 || bn > som::MAX_BN) return fail(SOM_ERR_ARG, "tile width must be a multiple of 16 within the kernel's range");
   som::GemmShape g;
-  g.M = static_cast<int>(M); g.N = static_cast<int>(N); g.Kred = static_cast<int>(Kred);
-  g.bn = bn; g.a_mn = a_mn ? 1 : 0; g.b_mn = b_mn ? 1 : 0;
-  g.kchunk = kchunk_req > 0 ? kchunk_req : g_kchunk.load();
-  g.passes = passes;
-  g.sk_workers = cg == 2 ? tc.sk_workers : 0;
-  g.sk_ws = ws;
-  g.debug = g_debug.load();
-  g.dbg_times = g_dbg_times.load();
-  g.tiles_m = static_cast<int>((M + som::BM * cg - 1) / (som::BM * cg));
-  g.tiles_n = static_cast<int>((N + bn - 1) / bn);
-  const size_t b_tile = g.b_mn ? static_cast<size_t>((b_rows + 31) / 32) * som::PANEL_BYTES : static_cast<size_t>(b_rows) * som::BK * 4;
+  fill_shape(g, p, 1, bn, kchunk, passes);
+  const size_t b_tile = g.b_mn ? static_cast<size_t>((bn + 31) / 32) * som::PANEL_BYTES : static_cast<size_t>(bn) * som::BK * 4;
   const size_t stage = 2 * som::A_TILE_BYTES + 2 * b_tile;
-  const size_t fixed = 1024 /*alignment slack*/ + som::BAR_REGION_BYTES +
-                       static_cast<size_t>(cg == 2 ? 8 : 4) * som::EPI_STG_FLOATS * sizeof(float);   // epilogue staging tiles
+  const size_t fixed = 1024 /*alignment slack*/ + som::BAR_REGION_BYTES;
   int nst = static_cast<int>((som::SMEM_LIMIT - fixed) / stage);
   if (nst > som::MAX_STAGES) nst = som::MAX_STAGES;
   if (nst < 2) return fail(SOM_ERR_ARG, "tile does not fit shared memory");
   g.nstages = nst;
   const size_t smem = fixed + nst * stage;
-
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
-  int rc;
-  if (g.a_mn) { if ((rc = make_tmap(&ta_hi, a_hi, M, Kred, lda, 32, true))) return rc; if ((rc = make_tmap(&ta_lo, a_lo ? a_lo : a_hi, M, Kred, lda, 32, true))) return rc; }
-  else        { if ((rc = make_tmap(&ta_hi, a_hi, Kred, M, lda, som::BM))) return rc; if ((rc = make_tmap(&ta_lo, a_lo ? a_lo : a_hi, Kred, M, lda, som::BM))) return rc; }
-  if (g.b_mn) { if ((rc = make_tmap(&tb_hi, b_hi, N, Kred, ldb, 32, true))) return rc; if ((rc = make_tmap(&tb_lo, b_lo ? b_lo : b_hi, N, Kred, ldb, 32, true))) return rc; }
-  else        { if ((rc = make_tmap(&tb_hi, b_hi, Kred, N, ldb, b_rows))) return rc; if ((rc = make_tmap(&tb_lo, b_lo ? b_lo : b_hi, Kred, N, ldb, b_rows))) return rc; }
-
+  if (int rc = make_problem_maps(p, som::BM, bn, &ta_hi, &ta_lo, &tb_hi, &tb_lo)) return rc;
   const int64_t nwork = static_cast<int64_t>(g.tiles_m) * g.tiles_n;
-  const int64_t slots = di.sms / cg;
-  const int grid = g.sk_workers > 0 ? g.sk_workers * cg : static_cast<int>(nwork < slots ? nwork : slots) * cg;
+  const int grid = static_cast<int>(nwork < sms ? nwork : sms);
   switch (epi) {
-    case som::EPI_RAW:  return launch_gemm_t<som::EPI_RAW>(ta_hi, ta_lo, tb_hi, tb_lo, g, e, cg, grid, smem, st);
-    case som::EPI_DIST: return launch_gemm_t<som::EPI_DIST>(ta_hi, ta_lo, tb_hi, tb_lo, g, e, cg, grid, smem, st);
-    case som::EPI_GRAD: return launch_gemm_t<som::EPI_GRAD>(ta_hi, ta_lo, tb_hi, tb_lo, g, e, cg, grid, smem, st);
+    case som::EPI_RAW:  return launch_single_t<som::EPI_RAW>(ta_hi, ta_lo, tb_hi, tb_lo, g, e, grid, smem, st);
+    case som::EPI_DIST: return launch_single_t<som::EPI_DIST>(ta_hi, ta_lo, tb_hi, tb_lo, g, e, grid, smem, st);
+    case som::EPI_GRAD: return launch_single_t<som::EPI_GRAD>(ta_hi, ta_lo, tb_hi, tb_lo, g, e, grid, smem, st);
   }
   return fail(SOM_ERR_ARG, "unknown epilogue");
 }
@@ -758,7 +872,7 @@ int launch_prep(const PrepSet& a, const PrepSet& b, int64_t dim, int mode, int64
 // ------------------------------------------------------------------------------------------------
 extern "C" {
 
-int som_b200_abi_version(void) { return 4; }
+int som_b200_abi_version(void) { return 5; }
 const char* som_last_error(void) { return g_last_error.c_str(); }
 int64_t som_launch_count(void) { return g_launches.load(); }
 void som_launch_count_reset(void) { g_launches.store(0); }
@@ -770,7 +884,7 @@ void som_set_debug(int bits) { g_debug.store(bits); }
 void som_set_debug_times(unsigned long long* dev_buf) { g_dbg_times.store(dev_buf); }
 void som_set_sm_limit(int max_sms) { g_sm_limit.store(max_sms > 0 ? max_sms : 0); }
 void som_set_streamk(int mode) { g_streamk.store(mode < 0 ? -1 : (mode > 0 ? 1 : 0)); }
-int64_t som_gemm_workspace_floats(void) { return 2ll * 74 * 256 * 256; }
+int64_t som_gemm_workspace_floats(void) { return SK_FLAG_WORDS + 74ll * 256 * 256; }
 void som_set_cta_group(int cg) { g_cg_override.store(cg == 1 || cg == 2 ? cg : 0); }
 
 int som_prep_rows(const float* src, int64_t rows, int64_t dim, int64_t ld_src, int mode, float* hi, float* lo,
@@ -999,6 +1113,62 @@ int som_backward_dx(const float* r_hi, const float* r_lo, int64_t ldr, const flo
   e.src = x; e.lds = ldx; e.out = dx; e.ldo = lddx;
   return launch_gemm(som::EPI_GRAD, r_hi, r_lo, ldr, 0, w_hi, w_lo, ld_stage, 1, B, D, K, 0, 0, 3, e, ws, ws_floats,
                      as_stream(stream));
+}
+
+// Both gradient GEMMs in ONE persistent CTA-pair launch: their tiles form one work list that stream-K spreads evenly
+// over the 74 pairs, so there is one prologue, one tail and no tile-count quantisation per GEMM.  Falls back to the two
+// separate launches when the shapes do not allow a common pair tile (tiny problems) or no workspace was given.
+int som_backward_fused(const float* r_hi, const float* r_lo, int64_t ldr, const float* x_hi, const float* x_lo,
+                       const float* w_hi, const float* w_lo, int64_t ld_stage, const float* x, int64_t ldx,
+                       const float* W, int64_t ldw, const float* row_sum, const float* col_sum, const float* x_aux,
+                       const float* w_aux, const float* g_dev, int64_t B, int64_t K, int64_t D, int mode, float* dW,
+                       int64_t lddw, int accumulate_dw, float* dx, int64_t lddx, float* ws, int64_t ws_floats,
+                       void* stream) {
+  if (!W || !col_sum || !x || !row_sum || !g_dev || !dW || !dx || ldw < D || lddw < D || ldx < D || lddx < D)
+    return fail(SOM_ERR_ARG, "som_backward_fused: bad argument");
+  if (mode != SOM_MODE_EUCLIDEAN && mode != SOM_MODE_COSINE) return fail(SOM_ERR_ARG, "som_backward_fused: bad mode");
+  if (mode == SOM_MODE_COSINE && (!w_aux || !x_aux)) return fail(SOM_ERR_ARG, "som_backward_fused: cosine needs the reciprocal norms");
+  int sms = 0;
+  if (int rc = effective_sms(&sms)) return rc;
+  if (ws && (reinterpret_cast<uintptr_t>(ws) & 15) != 0) return fail(SOM_ERR_ARG, "workspace must be 16-byte aligned");
+  Problem p[2];
+  // dW[K,D] = R^T[K,B] . x[B,D]: A = R read MN-major (K contiguous), B = x~ MN-major (D contiguous)
+  p[0] = Problem{r_hi, r_lo, ldr, 1, x_hi, x_lo, ld_stage, 1, K, D, B, som::EpiParams{}};
+  p[0].e.sum = col_sum; p[0].e.aux = w_aux; p[0].e.g_dev = g_dev; p[0].e.mode = mode; p[0].e.accumulate = accumulate_dw;
+  p[0].e.src = W; p[0].e.lds = ldw; p[0].e.out = dW; p[0].e.ldo = lddw;
+  // dx[B,D] = R[B,K] . W[K,D]: A = R K-major, B = W~ MN-major
+  p[1] = Problem{r_hi, r_lo, ldr, 0, w_hi, w_lo, ld_stage, 1, B, D, K, som::EpiParams{}};
+  p[1].e.sum = row_sum; p[1].e.aux = x_aux; p[1].e.g_dev = g_dev; p[1].e.mode = mode; p[1].e.accumulate = 0;
+  p[1].e.src = x; p[1].e.lds = ldx; p[1].e.out = dx; p[1].e.ldo = lddx;
+
+  // common tile width: the cheapest stream-K schedule of the joint work list (cost model of pick_tile)
+  const int forced_bn = g_bn_override.load();
+  const int64_t slots = sms / 2;
+  int best_bn = 0; int64_t best_workers = 0; double best_cost = 1e300;
+  if (ws && g_streamk.load() >= 0 && g_cg_override.load() != 1 && B > 128 && K > 128) {
+    for (int bn : {256, 192, 128, 64}) {
+      if (forced_bn && bn != forced_bn) continue;
+      int64_t units = 0, nkb_max = 1;
+      for (int i = 0; i < 2; ++i) {
+        const int64_t nkb = (p[i].Kred + som::BK - 1) / som::BK;
+        units += ((p[i].M + 255) / 256) * ((p[i].N + bn - 1) / bn) * nkb;
+        nkb_max = std::max(nkb_max, nkb);
+      }
+      const int64_t workers = streamk_workers(units, slots, bn, ws_floats);
+      if (workers < 2) continue;
+      const double cost = streamk_cost_ns(units, workers, nkb_max, bn);
+      if (cost < best_cost) { best_cost = cost; best_bn = bn; best_workers = workers; }
+    }
+  }
+  if (best_bn == 0) {
+    if (int rc = som_backward_dw(r_hi, r_lo, ldr, x_hi, x_lo, ld_stage, W, ldw, col_sum, w_aux, g_dev, B, K, D, mode, dW,
+                                 lddw, accumulate_dw, ws, ws_floats, stream))
+      return rc;
+    return som_backward_dx(r_hi, r_lo, ldr, w_hi, w_lo, ld_stage, x, ldx, row_sum, x_aux, g_dev, B, K, D, mode, dx, lddx,
+                           0, ws, ws_floats, stream);
+  }
+  return launch_pair(som::EPI_GRAD, p, 2, best_bn, static_cast<int>(best_workers), 0, pair_kchunk(g_kchunk.load(), 3),
+                     3, ws, sms, as_stream(stream));
 }
 
 int som_debug_gemm(const float* a_hi, const float* a_lo, int64_t lda, int a_mn, const float* b_hi, const float* b_lo,

@@ -24,6 +24,8 @@ MODE = {"euclidean": 0, "cosine": 1}
 # bench.py sets this to a list to get per-launch CUDA-event timings of the three tensor-core GEMMs
 # (entries: (name, start_event, end_event) recorded on the launching stream).
 GEMM_TIMERS = None
+# one persistent launch for both gradient GEMMs (som_backward_fused); False issues them separately
+FUSE_BACKWARD = True
 
 
 def _gemm(name, call):
@@ -175,7 +177,8 @@ def gemm_workspace(device):
     key = (device, torch.cuda.current_stream(device).cuda_stream)
     buf = _gemm_ws.get(key)
     if buf is None:
-        buf = torch.empty((int(_lib.lib().som_gemm_workspace_floats()),), device=device, dtype=torch.float32)
+        # zero-filled once: the head of the workspace holds the stream-K hand-over flags (the kernels restore zeros)
+        buf = torch.zeros((int(_lib.lib().som_gemm_workspace_floats()),), device=device, dtype=torch.float32)
         _gemm_ws[key] = buf
     return buf.data_ptr(), buf.numel()
 
@@ -241,8 +244,22 @@ class FusedLossFn(torch.autograd.Function):
         g = _grad_scalar(g_out)
         gws, gws_n = gemm_workspace(dev)
         dx = dw = join = None
+        acc_buf = st.grad_accum                 # row-chunked batches: the GEMM epilogue adds into this [K, D] buffer
+        if ctx.needs_input_grad[0] and ctx.needs_input_grad[1] and ctx.dw_hook is None and FUSE_BACKWARD:
+            # both gradients, nobody waiting for dW alone: ONE persistent launch over the tiles of both GEMMs
+            dw = acc_buf if acc_buf is not None else torch.empty((K, D), device=dev, dtype=torch.float32)
+            dx = torch.empty((B, D), device=dev, dtype=torch.float32)
+            check(_gemm("dw+dx", lambda: L.som_backward_fused(
+                r_hi, r_lo, ctx.ldr, st.xs.hi, st.xs.lo, st.ws.hi, st.ws.lo, st.xs.ld, ptr(st.x), st.x.stride(0),
+                ptr(st.W), st.W.stride(0), row_sum, col_sum, st.xs.aux, st.ws.aux, ptr(g), B, K, D, mode,
+                ptr(dw), dw.stride(0), 1 if acc_buf is not None else 0, ptr(dx), D, gws, gws_n, stream_ptr())),
+                "som_backward_fused")
+            if acc_buf is not None:
+                dw = None                       # already accumulated in place: nothing for autograd to add
+            if dx.dtype != ctx.x_dtype:
+                dx = dx.to(ctx.x_dtype)
+            return dx.view(ctx.x_shape), dw, None, None, None, None, None, None, None, None, None
         if ctx.needs_input_grad[1]:
-            acc_buf = st.grad_accum             # row-chunked batches: the GEMM epilogue adds into this [K, D] buffer
             dw = acc_buf if acc_buf is not None else torch.empty((K, D), device=dev, dtype=torch.float32)
             check(_gemm("dw", lambda: L.som_backward_dw(r_hi, r_lo, ctx.ldr, st.xs.hi, st.xs.lo, st.xs.ld, ptr(st.W),
                                                         st.W.stride(0), col_sum, st.ws.aux, ptr(g), B, K, D, mode,
