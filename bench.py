@@ -221,7 +221,7 @@ def main():
     ap.add_argument("--row-chunk", type=int, default=0,
                     help="rows per module call (0 = 4096, times the world size when prototypes are sharded)")
     ap.add_argument("--gemm-sms", type=int, default=-1,
-                    help="data parallel: SMs the GEMMs may occupy (0 = all, -1 = 128: ten TPCs stay free for NCCL)")
+                    help="data parallel: SMs the dx GEMM may occupy while the dW exchange runs (0 = all, -1 = 132)")
     args = ap.parse_args()
     wl = list(WORKLOADS[args.workload])
     if args.distance:
@@ -275,7 +275,7 @@ def main():
     if world > 1 and not sharded:              # batch-sharded DP: prototype-gradient all-reduce over NVLink,
         from vit_som_b200.distributed import DataParallelSOM
         # issued on a side stream from inside backward (runs under the dx GEMM, which leaves 20 SMs to NCCL)
-        gemm_sms = 128 if args.gemm_sms < 0 else args.gemm_sms
+        gemm_sms = 132 if args.gemm_sms < 0 else args.gemm_sms
         dp = DataParallelSOM(layer, gemm_sm_limit=gemm_sms if gemm_sms > 0 else None)
 
     def hot_path(xs):
@@ -391,6 +391,19 @@ def main():
                 c.copy_(x_host[ci * chunk:ci * chunk + c.shape[0]], non_blocking=True)
         copied[j].record(copy_stream)
 
+    # The step over each of the two staging buffers is captured once (vit_som_b200.StepGraph: the public helper a
+    # user of the layer calls) and replayed, so the host costs one graph launch per step; --no-graph issues the
+    # eager module calls.  Copies and read-backs stay outside the graphs, on the copy / compute streams.
+    e2e_graphs = None
+    if graph is not None:
+        try:
+            from vit_som_b200 import StepGraph
+            e2e_graphs = [StepGraph(lambda j=j: hot_path(x_stage[j]), warmup=1, stream=compute_stream) for j in range(2)]
+            torch.cuda.synchronize(dev)
+        except Exception as exc:  # noqa: BLE001
+            print(f"bench: e2e graph capture failed ({exc!r}); eager module calls", file=sys.stderr)
+            e2e_graphs = None
+            torch.cuda.synchronize(dev)
     for j in range(2):
         consumed[j].record(main_stream)
     e2e_start, e2e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -403,7 +416,7 @@ def main():
         if i + 1 < K_:
             prefetch(j ^ 1)
         main_stream.wait_event(copied[j])
-        loss = hot_path(x_stage[j])
+        loss = e2e_graphs[j].replay() if e2e_graphs is not None else hot_path(x_stage[j])
         consumed[j].record(main_stream)
         loss_host.copy_(loss, non_blocking=True)
     e2e_end.record()
@@ -467,7 +480,9 @@ def main():
         "dtype": "fp32 (3xTF32 tensor-core products, fp32 accumulate)", "data": "synthetic",
         "config": dict(workload_config(args.workload, wl, world, chunk, sharded), cuda_graph=graph is not None),
         "roofline": roofline,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": 4},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": 4,
+                "path": "vit_som_b200.StepGraph replay of the module-API step" if e2e_graphs is not None
+                else "eager module-API calls"},
         "gpu_launches": launches,
         "clocks": clocks.summary(),
     }

@@ -227,6 +227,19 @@ int som_backward_fused(const float* r_hi, const float* r_lo, int64_t ldr,
                        float* ws, int64_t ws_floats, void* stream);
 
 /*
+ * Exchange step of batch-sharded data parallelism (the reference gets it from Lightning DDP's bucketed NCCL
+ * all-reduce, experiments/benchmarking/train_vit_som.py:45,86-87): in-place MEAN over the ranks of the prototype
+ * gradient, as a two-shot NVLS (NVLink SHARP) all-reduce - multimem.ld_reduce of this rank's slice (summed in the
+ * NVSwitch), multimem.st of the mean to every replica - in one kernel with its own cross-GPU barriers.
+ *   mc_ptr    multicast address of the buffer (it lives at the same offset of a symmetric allocation on every rank)
+ *   flag_ptrs device array of `world` pointers to the ranks' zero-initialised flag buffers (peer mapped), each of at
+ *             least som_nvls_flag_words(world) 32-bit words; the kernel leaves them zero again
+ *   n_floats  multiple of 4.   Every rank of the group must make the call.
+ */
+int som_allreduce_mean_nvls(float* mc_ptr, void* flag_ptrs, int64_t n_floats, int rank, int world, void* stream);
+int64_t som_nvls_flag_words(int world);
+
+/*
  * Diagnostic entry point (used by the tests to validate the tensor-core mainloop in isolation):
  * C[M,N] = A . B^T in 3xTF32 with A = a_hi + a_lo, B = b_hi + b_lo.
  *   a_mn = 0: A stored [M, Kred] (K-major)    a_mn = 1: A stored [Kred, M] (MN-major)

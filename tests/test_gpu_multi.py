@@ -122,3 +122,45 @@ def _dp_worker(rank, world, fcn):
 @pytest.mark.parametrize("fcn", ["euclidean", "cosine"])
 def test_data_parallel_matches_oracle(fcn):
     spawn(_dp_worker, fcn)
+
+
+def _dp_repeat_worker(rank, world, mode):
+    """Several steps through the same DataParallelSOM (the NVLS barrier flags reset themselves; the symmetric dW buffer
+    is reused), NVLS against the NCCL all-reduce on the same inputs."""
+    import torch.distributed as dist
+    from vit_som_b200 import SOMLayer
+    from vit_som_b200.distributed import DataParallelSOM
+    ms, D, B, T = (16, 20), 264, 512, 3.0                 # K * D = 84480 floats: several blocks per rank slice
+    torch.manual_seed(7)
+    layer = SOMLayer(make_config(list(ms), D, "euclidean", Tmax=T)).cuda()
+    dp = DataParallelSOM(layer, nvls=None if mode == "auto" else False)
+    used_nvls = dp.nvls is not None
+    grads = []
+    for step in range(4):
+        x_np = np.random.RandomState(100 + step).randn(B, D).astype(np.float32)
+        r0, r1 = rank * B // world, (rank + 1) * B // world
+        x = torch.as_tensor(x_np[r0:r1]).cuda().requires_grad_(True)
+        layer.prototypes.grad = None
+        d, bmu = layer(x)
+        layer.som_loss(layer.compute_weights(bmu), d).backward()
+        torch.cuda.synchronize()
+        g = layer.prototypes.grad.clone()
+        W = layer.prototypes.detach().cpu().numpy()
+        ref = O.step(x_np, W, O.grid_positions(ms), T, "euclidean", 1.0, np.float64)
+        full_bmu = O.bmu(O.distances(x_np, W, "euclidean", np.float64))
+        same = torch.tensor([int((bmu.cpu().numpy() == full_bmu[r0:r1]).all())], device="cuda")
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        if int(same.item()):
+            assert O.rel_err(g.cpu().numpy(), ref.grad_w) < 1e-5, f"step {step} nvls={used_nvls}"
+        gathered = [torch.empty_like(g) for _ in range(world)]
+        dist.all_gather(gathered, g)
+        assert all(torch.equal(t, gathered[0]) for t in gathered)
+        grads.append(g)
+    torch.cuda.synchronize()
+    print(f"rank {rank}: data-parallel exchange path = {'NVLS multimem kernel' if used_nvls else 'NCCL all-reduce'}"
+          f"{'' if used_nvls or mode != 'auto' else ' (' + str(getattr(dp, 'nvls_error', 'no multicast')) + ')'}", flush=True)
+
+
+@pytest.mark.parametrize("mode", ["auto", "nccl"])
+def test_data_parallel_repeated_steps(mode):
+    spawn(_dp_repeat_worker, mode)

@@ -65,6 +65,8 @@ SIGNATURES = {
     "som_backward_fused": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, c_int64, _P, c_int64, _P, c_int64, _P, _P, _P, _P,
                                    _P, c_int64, c_int64, c_int64, c_int, _P, c_int64, c_int, _P, c_int64,
                                    _P, c_int64, _P]),
+    "som_allreduce_mean_nvls": (c_int, [_P, _P, c_int64, c_int, c_int, _P]),
+    "som_nvls_flag_words": (c_int64, [c_int]),
     "som_debug_gemm": (c_int, [_P, _P, c_int64, c_int, _P, _P, c_int64, c_int, c_int64, c_int64, c_int64,
                                c_int, c_int, c_int, _P, c_int64, _P, c_int64, _P]),
 }

@@ -850,6 +850,80 @@ inline int loss_rows_per_block(int64_t B, int64_t K, int sms) {
   return rpb;
 }
 
+
+// ----------------------------------------------------------------------------------------------
+// Prototype-gradient all-reduce over NVLink SHARP (NVLS): batch-sharded data parallelism averages dW[K, D] over the
+// ranks (DDP semantics, train_vit_som.py:45,86-87 via Lightning).  Every rank's dW lives at the same offset of a
+// symmetric allocation that the NVSwitch exposes as ONE multicast address.  Two-shot: rank r owns slice r of the
+// gradient; multimem.ld_reduce pulls that slice from all replicas, summed inside the switch; the mean goes back to
+// all replicas with one multimem.st.  Per rank 2 * n / world floats cross its links (NCCL's ring moves ~2 n), and
+// there is one kernel, one barrier before and one after, instead of a multi-step protocol.
+// Barrier: flags[world][channels][world] words in a second symmetric allocation; block b of rank r raises
+// flag[b][r] in every peer's copy (CAS 0 -> 1, release.sys) and lowers its own copy's flag[b][peer] (CAS 1 -> 0,
+// acquire.sys): self-resetting, so launches (and CUDA-graph replays) can follow each other without host involvement.
+// ----------------------------------------------------------------------------------------------
+constexpr int NVLS_BLOCKS = 32;
+constexpr int NVLS_UNROLL = 8;
+constexpr int NVLS_THREADS = 512;
+
+__device__ __forceinline__ void nvls_signal(unsigned int* addr) {
+  const long long t0 = clock64();
+  unsigned int seen;
+  do {
+    asm volatile("atom.global.release.sys.cas.b32 %0, [%1], 0, 1;" : "=r"(seen) : "l"(addr) : "memory");
+    if (seen != 0u && clock64() - t0 > 6000000000LL) { printf("som_b200: NVLS barrier signal timed out\n"); __trap(); }
+  } while (seen != 0u);
+}
+__device__ __forceinline__ void nvls_wait(unsigned int* addr) {
+  const long long t0 = clock64();
+  unsigned int seen;
+  do {
+    asm volatile("atom.global.acquire.sys.cas.b32 %0, [%1], 1, 0;" : "=r"(seen) : "l"(addr) : "memory");
+    if (seen != 1u && clock64() - t0 > 6000000000LL) { printf("som_b200: NVLS barrier wait timed out\n"); __trap(); }
+  } while (seen != 1u);
+}
+// All blocks with the same blockIdx on all ranks meet.  flag_ptrs[p] = rank p's flag buffer (peer mapped).
+__device__ __forceinline__ void nvls_block_barrier(unsigned int* const* flag_ptrs, int rank, int world) {
+  __syncthreads();
+  if (threadIdx.x < world) {
+    const int peer = threadIdx.x;
+    nvls_signal(flag_ptrs[peer] + (blockIdx.x * world + rank));
+    nvls_wait(flag_ptrs[rank] + (blockIdx.x * world + peer));
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(NVLS_THREADS)
+nvls_allreduce_mean_kernel(float* mc, unsigned int* const* flag_ptrs, long long n4, int rank, int world, float scale) {
+  nvls_block_barrier(flag_ptrs, rank, world);            // every rank's dW is complete and visible
+  const long long per = (n4 + world - 1) / world;        // float4 elements per rank slice
+  const long long begin = per * rank, end = begin + per < n4 ? begin + per : n4;
+  // NVLS_UNROLL independent 16-byte reductions in flight per thread: a multimem.ld_reduce is a round trip through
+  // the switch (~2-3 us), so the bytes in flight set the throughput (one per thread gave ~65 GB/s)
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i0 = begin + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < end;
+       i0 += stride * NVLS_UNROLL) {
+    float4 v[NVLS_UNROLL];
+#pragma unroll
+    for (int u = 0; u < NVLS_UNROLL; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < end)
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "l"(mc + 4 * i) : "memory");
+    }
+#pragma unroll
+    for (int u = 0; u < NVLS_UNROLL; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < end)
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                     ::"l"(mc + 4 * i), "f"(v[u].x * scale), "f"(v[u].y * scale), "f"(v[u].z * scale), "f"(v[u].w * scale)
+                     : "memory");
+    }
+  }
+  __threadfence_system();
+  nvls_block_barrier(flag_ptrs, rank, world);            // every slice has reached every replica
+}
+
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 int launch_prep(const PrepSet& a, const PrepSet& b, int64_t dim, int mode, int64_t ld_out, cudaStream_t st) {
@@ -1170,6 +1244,26 @@ int som_backward_fused(const float* r_hi, const float* r_lo, int64_t ldr, const 
   return launch_pair(som::EPI_GRAD, p, 2, best_bn, static_cast<int>(best_workers), 0, pair_kchunk(g_kchunk.load(), 3),
                      3, ws, sms, as_stream(stream));
 }
+
+// In-place mean over the ranks of the fp32 buffer every rank holds at the same offset of a symmetric allocation:
+//   mc_ptr    : the MULTICAST address of the buffer (NVLS; e.g. torch symmetric memory, handle.multicast_ptr)
+//   flag_ptrs : device array of `world` pointers, flag_ptrs[p] = rank p's zero-initialised flag buffer of at least
+//               som_nvls_flag_words(world) 32-bit words (peer-mapped symmetric allocation)
+//   n_floats  : multiple of 4
+// Must be launched by every rank of the group (it contains cross-GPU barriers); enqueues one kernel on `stream`.
+int som_allreduce_mean_nvls(float* mc_ptr, void* flag_ptrs, int64_t n_floats, int rank, int world, void* stream) {
+  DeviceInfo di;
+  if (int rc = device_info(di)) return rc;
+  if (!mc_ptr || !flag_ptrs || n_floats <= 0 || (n_floats & 3) != 0 || world < 1 || world > 32 || rank < 0 || rank >= world)
+    return fail(SOM_ERR_ARG, "som_allreduce_mean_nvls: bad argument");
+  if ((reinterpret_cast<uintptr_t>(mc_ptr) & 15) != 0) return fail(SOM_ERR_ARG, "som_allreduce_mean_nvls: misaligned buffer");
+  nvls_allreduce_mean_kernel<<<NVLS_BLOCKS, NVLS_THREADS, 0, as_stream(stream)>>>(
+      mc_ptr, reinterpret_cast<unsigned int* const*>(flag_ptrs), n_floats / 4, rank, world, 1.0f / static_cast<float>(world));
+  SOM_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return SOM_OK;
+}
+int64_t som_nvls_flag_words(int world) { return static_cast<int64_t>(NVLS_BLOCKS) * (world > 0 ? world : 1); }
 
 int som_debug_gemm(const float* a_hi, const float* a_lo, int64_t lda, int a_mn, const float* b_hi, const float* b_lo,
                    int64_t ldb, int b_mn, int64_t M, int64_t N, int64_t Kred, int bn, int kchunk, int passes, float* C,

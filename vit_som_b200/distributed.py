@@ -19,6 +19,8 @@ work stays in libsom_b200.so.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -85,13 +87,14 @@ class DataParallelSOM:
     communication stream; the dx GEMM then runs concurrently, and the compute stream joins the communication stream
     before backward returns dW to autograd.  The local loss is the mean over the local rows, as under DDP."""
 
-    def __init__(self, layer: SOMLayer, group=None, broadcast: bool = True, gemm_sm_limit: int | None = None):
+    def __init__(self, layer: SOMLayer, group=None, broadcast: bool = True, gemm_sm_limit: int | None = None,
+                 nvls: bool | None = None):
         if not dist.is_initialized():
             raise SomError("DataParallelSOM needs an initialised torch.distributed process group")
         self.layer, self.group = layer, group
-        if gemm_sm_limit is not None and layer.prototypes.is_cuda:
-            from . import _lib
-            _lib.lib().som_set_sm_limit(int(gemm_sm_limit))   # leave TPCs free for the NCCL kernels (see som_b200.h)
+        self.nvls = None
+        # SMs the dx GEMM may occupy while the exchange runs next to it (the other GEMMs of the step use all SMs)
+        self.gemm_sm_limit = int(gemm_sm_limit) if gemm_sm_limit is not None and layer.prototypes.is_cuda else 0
         self.world = dist.get_world_size(group)
         dev = layer.prototypes.device
         # lowest priority: when dW's all-reduce and the dx GEMM become runnable together the GEMM's CTA pairs are
@@ -102,6 +105,44 @@ class DataParallelSOM:
                 dist.broadcast(layer.prototypes.data, src=dist.get_global_rank(group, 0) if group is not None else 0,
                                group=group)
         layer._dw_hook = self._on_dw
+        want_nvls = nvls if nvls is not None else os.environ.get("SOM_DP_NVLS", "1") != "0"
+        if want_nvls and dev.type == "cuda" and self.world > 1:
+            self.nvls = self._setup_nvls(layer, dev)
+            if nvls and self.nvls is None:
+                raise SomError("NVLS all-reduce requested but symmetric multicast memory is not available")
+
+    # ---- NVLS (NVLink SHARP) exchange: our own two-shot multimem kernel over torch symmetric memory -------------
+    def _setup_nvls(self, layer, dev):
+        """Allocate dW and the barrier flags in symmetric memory and rendezvous; None when multicast is unavailable
+        (then the NCCL all-reduce is used).  Every rank takes the same decision (it is all-reduced)."""
+        state = None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            from . import _lib
+            grp = self.group if self.group is not None else dist.group.WORLD
+            K, D = layer.prototypes.shape
+            n = K * D
+            if n % 4 == 0:
+                dw = symm_mem.empty((K, D), dtype=torch.float32, device=dev)
+                hdl = symm_mem.rendezvous(dw, grp)
+                words = int(_lib.lib().som_nvls_flag_words(self.world))
+                flags = symm_mem.empty((max(words, 1024),), dtype=torch.int32, device=dev)
+                flags.zero_()
+                fh = symm_mem.rendezvous(flags, grp)
+                if int(getattr(hdl, "multicast_ptr", 0) or 0) != 0:
+                    state = {"dw": dw, "hdl": hdl, "flags": flags, "fh": fh, "n": n,
+                             "mc": int(hdl.multicast_ptr), "flag_ptrs": int(fh.buffer_ptrs_dev)}
+        except Exception as exc:  # noqa: BLE001
+            self.nvls_error = repr(exc)
+            state = None
+        ok = torch.tensor([1 if state is not None else 0], device=dev, dtype=torch.int32)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        torch.cuda.synchronize(dev)
+        if int(ok.item()) == 0:
+            return None
+        dist.barrier(group=self.group)                       # flags are zero everywhere before the first kernel
+        layer._dw_out = state["dw"]
+        return state
 
     def _on_dw(self, dw: torch.Tensor):
         """Called from FusedLossFn.backward with the freshly enqueued dW; returns the join callable."""
@@ -111,12 +152,28 @@ class DataParallelSOM:
         cur = torch.cuda.current_stream(dw.device)
         self.comm_stream.wait_stream(cur)
         with torch.cuda.stream(self.comm_stream):
-            all_reduce_mean(dw, self.group)
+            nv = self.nvls
+            if nv is not None and dw.data_ptr() == nv["dw"].data_ptr():
+                from . import _lib
+                _lib.check(_lib.lib().som_allreduce_mean_nvls(nv["mc"], nv["flag_ptrs"], nv["n"], dist.get_rank(self.group),
+                                                              self.world, _lib.stream_ptr()), "som_allreduce_mean_nvls")
+            else:
+                all_reduce_mean(dw, self.group)
         dw.record_stream(self.comm_stream)
+        if self.gemm_sm_limit:
+            from . import _lib
+            L = _lib.lib()
+            L.som_set_sm_limit(self.gemm_sm_limit)         # host-side launch parameter of the dx GEMM that follows
+
+            def join():
+                L.som_set_sm_limit(0)
+                cur.wait_stream(self.comm_stream)
+            return join
         return lambda: cur.wait_stream(self.comm_stream)
 
     def detach(self):
         self.layer._dw_hook = None
+        self.layer._dw_out = None
 
 
 # ------------------------------------------------------------------------------------------------------------

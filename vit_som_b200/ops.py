@@ -95,7 +95,7 @@ def stage_rows(src: torch.Tensor, mode: int) -> Staging:
 class ForwardState:
     """What one forward leaves behind for the loss and the backward: raw and staged operands and the distances."""
     __slots__ = ("x", "W", "xs", "ws", "mode", "B", "K", "D", "dist_buf", "ldd", "packed", "idx_offset",
-                 "x_in", "W_in", "grad_accum")
+                 "x_in", "W_in", "grad_accum", "dw_out")
 
 
 def forward(x: torch.Tensor, W: torch.Tensor, mode: int, ws: Staging | None = None, stage_w: bool = True,
@@ -148,6 +148,7 @@ def forward(x: torch.Tensor, W: torch.Tensor, mode: int, ws: Staging | None = No
     st.x, st.W, st.xs, st.ws, st.mode = xf, Wf, xs, ws, mode
     st.B, st.K, st.D, st.dist_buf, st.ldd, st.packed, st.idx_offset = B, K, D, dist_buf, ldd, packed, idx_offset
     st.grad_accum = None
+    st.dw_out = None             # optional caller-owned [K, D] destination of dW (data parallel: a symmetric buffer)
     return st, bmu
 
 
@@ -260,7 +261,8 @@ class FusedLossFn(torch.autograd.Function):
                 dx = dx.to(ctx.x_dtype)
             return dx.view(ctx.x_shape), dw, None, None, None, None, None, None, None, None, None
         if ctx.needs_input_grad[1]:
-            dw = acc_buf if acc_buf is not None else torch.empty((K, D), device=dev, dtype=torch.float32)
+            dw = acc_buf if acc_buf is not None else (
+                st.dw_out if st.dw_out is not None else torch.empty((K, D), device=dev, dtype=torch.float32))
             check(_gemm("dw", lambda: L.som_backward_dw(r_hi, r_lo, ctx.ldr, st.xs.hi, st.xs.lo, st.xs.ld, ptr(st.W),
                                                         st.W.stride(0), col_sum, st.ws.aux, ptr(g), B, K, D, mode,
                                                         ptr(dw), dw.stride(0), 1 if acc_buf is not None else 0,

@@ -116,6 +116,7 @@ class SOMLayer(_Base):
         # and returns no gradient for `prototypes` to autograd (row-chunked batches accumulate without extra passes)
         self.grad_accumulator = None
         self._dw_hook = None                                              # data-parallel wrapper: called with dW as soon as it is enqueued
+        self._dw_out = None                                               # data-parallel wrapper: [K, D] buffer the dW GEMM writes (NVLS symmetric memory)
 
     # ---- construction helpers -----------------------------------------------------------------
     def create_grid_positions(self):
@@ -173,6 +174,7 @@ class SOMLayer(_Base):
             return None, bmu
         state.x_in, state.W_in = x, self.prototypes
         state.grad_accum = self.grad_accumulator
+        state.dw_out = self._dw_out
         dist = ops.DistanceFn.apply(x, self.prototypes, state)
         dist._som_state = state                          # lets som_loss take the fused path (no B x K autograd edge)
         return dist, bmu
