@@ -413,9 +413,22 @@ prep_rows_kernel(const PrepSet sa, const PrepSet sb, long long blocks_a, int dim
   const float* p = src + (active ? row : 0) * ld_src;
   const bool vec = (dim & 3) == 0 && (ld_src & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
 
+  // rows of up to PREP_CACHE * GROUP * 4 elements are read ONCE: the values wait in registers for the row norm
+  constexpr int PREP_CACHE = 8;
+  const bool cached = vec && dim <= PREP_CACHE * GROUP * 4;
+  float4 cache[PREP_CACHE];
   float ss = 0.f;
   if (active) {
-    if (vec) {
+    if (cached) {
+#pragma unroll
+      for (int j = 0; j < PREP_CACHE; ++j) {
+        const int i = (gt + j * GROUP) * 4;
+        cache[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < dim) cache[j] = __ldg(reinterpret_cast<const float4*>(p + i));
+        const float4 v = cache[j];
+        ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+      }
+    } else if (vec) {
       for (int i = gt * 4; i < dim; i += GROUP * 4) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(p + i));
         ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
@@ -444,15 +457,26 @@ prep_rows_kernel(const PrepSet sa, const PrepSet sb, long long blocks_a, int dim
   float* ph = hi + row * ld_out;
   float* pl = lo + row * ld_out;
   const int dim_out = static_cast<int>(ld_out);
-  if (vec) {
+  auto split4 = [&](float4 v, float4& h, float4& l) {
+    if (mode == 1) { v.x = v.x / denom; v.y = v.y / denom; v.z = v.z / denom; v.w = v.w / denom; }
+    h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+    l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+  };
+  if (cached) {
+#pragma unroll
+    for (int j = 0; j < PREP_CACHE; ++j) {
+      const int i = (gt + j * GROUP) * 4;
+      if (i < dim_out) {
+        float4 h = make_float4(0.f, 0.f, 0.f, 0.f), l = h;
+        if (i < dim) split4(cache[j], h, l);
+        *reinterpret_cast<float4*>(ph + i) = h;
+        *reinterpret_cast<float4*>(pl + i) = l;
+      }
+    }
+  } else if (vec) {
     for (int i = gt * 4; i < dim_out; i += GROUP * 4) {
       float4 h = make_float4(0.f, 0.f, 0.f, 0.f), l = h;
-      if (i < dim) {
-        float4 v = __ldg(reinterpret_cast<const float4*>(p + i));
-        if (mode == 1) { v.x = v.x / denom; v.y = v.y / denom; v.z = v.z / denom; v.w = v.w / denom; }
-        h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-        l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
-      }
+      if (i < dim) split4(__ldg(reinterpret_cast<const float4*>(p + i)), h, l);
       *reinterpret_cast<float4*>(ph + i) = h;
       *reinterpret_cast<float4*>(pl + i) = l;
     }
