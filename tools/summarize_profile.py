@@ -46,7 +46,7 @@ def launches(tag, out):
     step = None
     for a, b in zip(starts, starts[1:]):
         seg = recs[a:b]
-        if sum("gemm3x" in r[0] for r in seg) == 3:
+        if sum("gemm3x" in r[0] for r in seg) in (2, 3) and sum("prep_rows" in r[0] for r in seg) == 1:
             step = seg
     with open(out, "w") as f:
         f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none; python bench.py --steps 2 --warmup 3 "
@@ -75,7 +75,7 @@ def kernels(tag, out, workload):
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
     idx = {h: i for i, h in enumerate(hdr)}
-    gemm_traffic = []
+    gemm_traffic = {}
     with open(out, "w") as f:
         f.write(f"# ncu --set full --clock-control none --import-source on (tag {tag}); one launch per block below.\n")
         f.write("# Captured under the profiler (serialised, cold L2): use for ratios and traffic, not for timing claims.\n")
@@ -88,15 +88,18 @@ def kernels(tag, out, workload):
             if "gemm3x" in name:
                 conv = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}
                 tr = sum(float(d[idx[m]]) * conv[units[idx[m]]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-                gemm_traffic.append(tr)
+                gemm_traffic.setdefault(name, []).append(tr)
     if gemm_traffic:
         tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
         cur = {}
         if os.path.exists(tpath):
             with open(tpath) as f:
                 cur = json.load(f)
-        cur[workload] = {"dram_bytes_per_launch": sum(gemm_traffic) / len(gemm_traffic),
-                         "launches_averaged": len(gemm_traffic), "source": f"profiles/{tag}_ncu_kernels.txt"}
+        # one step = one launch of each GEMM kernel (forward, fused backward): average over the kinds
+        per_kind = {k: sum(v) / len(v) for k, v in gemm_traffic.items()}
+        cur[workload] = {"dram_bytes_per_launch": sum(per_kind.values()) / len(per_kind),
+                         "per_kernel": per_kind, "note": "ncu --set full, cold L2 (flushed before every replay pass)",
+                         "source": f"profiles/{tag}_ncu_kernels.txt"}
         with open(tpath, "w") as f:
             json.dump(cur, f, indent=1)
 
