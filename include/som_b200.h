@@ -237,6 +237,8 @@ int som_backward_fused(const float* r_hi, const float* r_lo, int64_t ldr,
  *   n_floats  multiple of 4.   Every rank of the group must make the call.
  */
 int som_allreduce_mean_nvls(float* mc_ptr, void* flag_ptrs, int64_t n_floats, int rank, int world, void* stream);
+/* The same kernel with an explicit factor (1.0f = SUM): the partial dx[B,D] of prototype shards. */
+int som_allreduce_nvls(float* mc_ptr, void* flag_ptrs, int64_t n_floats, int rank, int world, float scale, void* stream);
 int64_t som_nvls_flag_words(int world);
 
 /*
@@ -251,6 +253,12 @@ int som_debug_gemm(const float* a_hi, const float* a_lo, int64_t lda, int a_mn,
                    const float* b_hi, const float* b_lo, int64_t ldb, int b_mn,
                    int64_t M, int64_t N, int64_t Kred, int bn, int kchunk, int passes,
                    float* C, int64_t ldc, float* ws, int64_t ws_floats, void* stream);
+
+/* Diagnostics, host only: the work decomposition of the CTA-pair kernel for `workers` CTA pairs over the k-block units
+ * of one or two GEMMs (tiles x k-blocks each; tiles1 = 0 for one GEMM).  split > 0: tile-aligned split-K, else even
+ * ranges (stream-K).  bounds_out[0..workers]: first unit of every worker, then the total. */
+int som_debug_schedule(int64_t tiles0, int64_t nkb0, int64_t tiles1, int64_t nkb1, int workers, int split,
+                       int64_t* bounds_out);
 
 /* Tuning knobs (process-wide): tile width override (0 = auto) and k-blocks per accumulation chunk. */
 void som_set_tuning(int bn_override, int kchunk);

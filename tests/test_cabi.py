@@ -64,3 +64,42 @@ def test_no_gpu_means_loud_failure_not_fallback(lib):
     layer = SOMLayer(make_config([4, 4], 8))
     with pytest.raises(SomError):
         layer(torch.randn(3, 8))
+
+
+def _bounds(lib, tiles0, nkb0, tiles1, nkb1, workers, split):
+    import ctypes
+    out = (ctypes.c_int64 * (workers + 1))()
+    assert lib.som_debug_schedule(tiles0, nkb0, tiles1, nkb1, workers, split, out) == 0
+    return list(out)
+
+
+def test_streamk_ranges_partition_the_work(lib):
+    """The k-block ranges of the CTA pairs (host view of the device scheduler) cover every unit exactly once, in
+    order, for one and two GEMMs per launch."""
+    import random
+    rng = random.Random(0)
+    for _ in range(200):
+        tiles0, nkb0 = rng.randint(1, 300), rng.randint(1, 200)
+        two = rng.random() < 0.5
+        tiles1, nkb1 = (rng.randint(1, 300), rng.randint(1, 200)) if two else (0, 0)
+        workers = rng.randint(2, 74)
+        b = _bounds(lib, tiles0, nkb0, tiles1, nkb1, workers, 0)
+        total = tiles0 * nkb0 + tiles1 * nkb1
+        assert b[0] == 0 and b[-1] == total
+        assert all(x <= y for x, y in zip(b, b[1:]))
+        sizes = [y - x for x, y in zip(b, b[1:])]
+        assert max(sizes) - min(sizes) <= 1                       # even ranges
+
+
+def test_splitk_pieces_are_tile_aligned(lib):
+    """Split-K: worker p = tile * split + piece; pieces of a tile are contiguous, the owner's (piece 0) starts at
+    the tile's first k-block and is the longest (it waits for the others)."""
+    for tiles, nkb, split in [(36, 98, 2), (10, 40, 3), (5, 64, 2), (7, 200, 4)]:
+        workers = tiles * split
+        b = _bounds(lib, tiles, nkb, 0, 0, workers, split)
+        assert b[0] == 0 and b[-1] == tiles * nkb
+        assert all(x <= y for x, y in zip(b, b[1:]))
+        for t in range(tiles):
+            assert b[t * split] == t * nkb                        # owner starts at the tile's head
+            pieces = [b[t * split + i + 1] - b[t * split + i] for i in range(split)]
+            assert sum(pieces) == nkb and pieces[0] == max(pieces)

@@ -1275,19 +1275,39 @@ int som_backward_fused(const float* r_hi, const float* r_lo, int64_t ldr, const 
 //               som_nvls_flag_words(world) 32-bit words (peer-mapped symmetric allocation)
 //   n_floats  : multiple of 4
 // Must be launched by every rank of the group (it contains cross-GPU barriers); enqueues one kernel on `stream`.
-int som_allreduce_mean_nvls(float* mc_ptr, void* flag_ptrs, int64_t n_floats, int rank, int world, void* stream) {
+int som_allreduce_nvls(float* mc_ptr, void* flag_ptrs, int64_t n_floats, int rank, int world, float scale, void* stream) {
   DeviceInfo di;
   if (int rc = device_info(di)) return rc;
   if (!mc_ptr || !flag_ptrs || n_floats <= 0 || (n_floats & 3) != 0 || world < 1 || world > 32 || rank < 0 || rank >= world)
-    return fail(SOM_ERR_ARG, "som_allreduce_mean_nvls: bad argument");
-  if ((reinterpret_cast<uintptr_t>(mc_ptr) & 15) != 0) return fail(SOM_ERR_ARG, "som_allreduce_mean_nvls: misaligned buffer");
+    return fail(SOM_ERR_ARG, "som_allreduce_nvls: bad argument");
+  if ((reinterpret_cast<uintptr_t>(mc_ptr) & 15) != 0) return fail(SOM_ERR_ARG, "som_allreduce_nvls: misaligned buffer");
   nvls_allreduce_mean_kernel<<<NVLS_BLOCKS, NVLS_THREADS, 0, as_stream(stream)>>>(
-      mc_ptr, reinterpret_cast<unsigned int* const*>(flag_ptrs), n_floats / 4, rank, world, 1.0f / static_cast<float>(world));
+      mc_ptr, reinterpret_cast<unsigned int* const*>(flag_ptrs), n_floats / 4, rank, world, scale);
   SOM_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
   return SOM_OK;
 }
+int som_allreduce_mean_nvls(float* mc_ptr, void* flag_ptrs, int64_t n_floats, int rank, int world, void* stream) {
+  return som_allreduce_nvls(mc_ptr, flag_ptrs, n_floats, rank, world, 1.0f / static_cast<float>(world > 0 ? world : 1), stream);
+}
 int64_t som_nvls_flag_words(int world) { return static_cast<int64_t>(NVLS_BLOCKS) * (world > 0 ? world : 1); }
+
+// Host-side view of the CTA-pair kernel's work decomposition (the same sk_bound() the device code evaluates):
+// bounds_out[p] = first k-block unit of worker p, bounds_out[workers] = total units.  Pure host code (tests).
+int som_debug_schedule(int64_t tiles0, int64_t nkb0, int64_t tiles1, int64_t nkb1, int workers, int split,
+                       int64_t* bounds_out) {
+  if (tiles0 <= 0 || nkb0 <= 0 || tiles1 < 0 || (tiles1 > 0 && nkb1 <= 0) || workers <= 0 || !bounds_out)
+    return fail(SOM_ERR_ARG, "som_debug_schedule: bad argument");
+  som::Sched s;
+  s.nprob = tiles1 > 0 ? 2 : 1;
+  s.nkb0 = static_cast<int>(nkb0); s.tiles0 = static_cast<int>(tiles0);
+  s.nkb1 = tiles1 > 0 ? static_cast<int>(nkb1) : 1; s.tiles1 = static_cast<int>(tiles1);
+  s.units0 = tiles0 * nkb0;
+  s.units = s.units0 + tiles1 * (tiles1 > 0 ? nkb1 : 0);
+  s.split = split;
+  for (int p = 0; p <= workers; ++p) bounds_out[p] = som::sk_bound(s, workers, p);
+  return SOM_OK;
+}
 
 int som_debug_gemm(const float* a_hi, const float* a_lo, int64_t lda, int a_mn, const float* b_hi, const float* b_lo,
                    int64_t ldb, int b_mn, int64_t M, int64_t N, int64_t Kred, int bn, int kchunk, int passes, float* C,

@@ -188,6 +188,7 @@ class _ShardedLossFn(torch.autograd.Function):
         loss = ops.FusedLossFn.forward(ctx, x, W, state, bmu, grid_pos, T_dev, inv_count, k_offset, want_grad, None,
                                        grid_dims)
         ctx.group = group
+        ctx.nvls = getattr(state, "nvls_dx", None)
         return all_reduce_sum(loss, group)
 
     @staticmethod
@@ -195,7 +196,16 @@ class _ShardedLossFn(torch.autograd.Function):
         grads = ops.FusedLossFn.backward(ctx, g_out)
         dx = grads[0]
         if dx is not None:
-            all_reduce_sum(dx, ctx.group)
+            nv = ctx.nvls
+            if nv is not None and dx.data_ptr() == nv["buf"].data_ptr() and dx.dtype == torch.float32:
+                # partial dx of all shards summed in the NVSwitch (our two-shot multimem kernel), in place in the
+                # symmetric buffer; autograd gets a private copy because the buffer is reused by the next call
+                from . import _lib
+                _lib.check(_lib.lib().som_allreduce_nvls(nv["mc"], nv["flag_ptrs"], nv["n"], nv["rank"], nv["world"],
+                                                         1.0, _lib.stream_ptr()), "som_allreduce_nvls")
+                grads = (dx.clone(),) + tuple(grads[1:])
+            else:
+                all_reduce_sum(dx, ctx.group)
         return grads[:11]
 
 
@@ -219,6 +229,44 @@ class PrototypeShardedSOM(SOMLayer):
             raise ValueError(f"map of {self.k_total} cells cannot be sharded over {self.world} ranks")
         full = self.prototypes.data
         self.prototypes = torch.nn.Parameter(full[self.k_begin:self.k_end].clone())
+        self._nvls_dx = {}                    # (B, D) -> symmetric dx buffer + multicast mapping (None: NCCL)
+        self.use_nvls = os.environ.get("SOM_DP_NVLS", "1") != "0"
+
+    def _nvls_dx_buffer(self, B: int, D: int, dev):
+        """Symmetric [B, D] buffer for the partial dx of this rank plus what som_allreduce_nvls needs; allocated and
+        rendezvoused once per shape (a collective: every rank reaches it with the same shape at the same call)."""
+        key = (B, D)
+        if key in self._nvls_dx:
+            return self._nvls_dx[key]
+        state = None
+        if self.use_nvls and dev.type == "cuda" and self.world > 1 and (B * D) % 4 == 0:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                from . import _lib
+                grp = self.group if self.group is not None else dist.group.WORLD
+                buf = symm_mem.empty((B, D), dtype=torch.float32, device=dev)
+                hdl = symm_mem.rendezvous(buf, grp)
+                if not hasattr(self, "_nvls_flags"):
+                    words = int(_lib.lib().som_nvls_flag_words(self.world))
+                    flags = symm_mem.empty((max(words, 1024),), dtype=torch.int32, device=dev)
+                    flags.zero_()
+                    self._nvls_flags = (flags, symm_mem.rendezvous(flags, grp))
+                if int(getattr(hdl, "multicast_ptr", 0) or 0) != 0:
+                    state = {"buf": buf, "hdl": hdl, "n": B * D, "mc": int(hdl.multicast_ptr),
+                             "flag_ptrs": int(self._nvls_flags[1].buffer_ptrs_dev), "rank": self.rank, "world": self.world}
+            except Exception as exc:  # noqa: BLE001
+                self.nvls_error = repr(exc)
+                state = None
+            ok = torch.tensor([1 if state is not None else 0], device=dev, dtype=torch.int32)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if int(ok.item()) == 0:
+                state = None
+                self.use_nvls = False
+            else:
+                torch.cuda.synchronize(dev)
+                dist.barrier(group=self.group)           # flags are zero everywhere before the first kernel
+        self._nvls_dx[key] = state
+        return state
 
     def _forward_impl(self, x, want_dist=True):
         if x.dim() > 2:
@@ -241,6 +289,13 @@ class PrototypeShardedSOM(SOMLayer):
             return None, bmu
         state.x_in, state.W_in = x, self.prototypes
         state.grad_accum = self.grad_accumulator
+        state.nvls_dx = None
+        if torch.is_grad_enabled() and x.requires_grad and not torch.cuda.is_current_stream_capturing():
+            nv = self._nvls_dx_buffer(state.B, state.D, x.device)
+        else:
+            nv = self._nvls_dx.get((state.B, state.D))   # capture / no_grad: only what already exists
+        if nv is not None:
+            state.dx_out, state.nvls_dx = nv["buf"], nv
         dist_local = ops.DistanceFn.apply(x, self.prototypes, state)
         dist_local._som_state = state
         return dist_local, bmu

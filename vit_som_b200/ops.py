@@ -95,7 +95,7 @@ def stage_rows(src: torch.Tensor, mode: int) -> Staging:
 class ForwardState:
     """What one forward leaves behind for the loss and the backward: raw and staged operands and the distances."""
     __slots__ = ("x", "W", "xs", "ws", "mode", "B", "K", "D", "dist_buf", "ldd", "packed", "idx_offset",
-                 "x_in", "W_in", "grad_accum", "dw_out")
+                 "x_in", "W_in", "grad_accum", "dw_out", "dx_out", "nvls_dx")
 
 
 def forward(x: torch.Tensor, W: torch.Tensor, mode: int, ws: Staging | None = None, stage_w: bool = True,
@@ -149,6 +149,8 @@ def forward(x: torch.Tensor, W: torch.Tensor, mode: int, ws: Staging | None = No
     st.B, st.K, st.D, st.dist_buf, st.ldd, st.packed, st.idx_offset = B, K, D, dist_buf, ldd, packed, idx_offset
     st.grad_accum = None
     st.dw_out = None             # optional caller-owned [K, D] destination of dW (data parallel: a symmetric buffer)
+    st.dx_out = None             # optional caller-owned [B, D] destination of dx (prototype shards: a symmetric buffer)
+    st.nvls_dx = None
     return st, bmu
 
 
@@ -249,7 +251,7 @@ class FusedLossFn(torch.autograd.Function):
         if ctx.needs_input_grad[0] and ctx.needs_input_grad[1] and ctx.dw_hook is None and FUSE_BACKWARD:
             # both gradients, nobody waiting for dW alone: ONE persistent launch over the tiles of both GEMMs
             dw = acc_buf if acc_buf is not None else torch.empty((K, D), device=dev, dtype=torch.float32)
-            dx = torch.empty((B, D), device=dev, dtype=torch.float32)
+            dx = st.dx_out if st.dx_out is not None else torch.empty((B, D), device=dev, dtype=torch.float32)
             check(_gemm("dw+dx", lambda: L.som_backward_fused(
                 r_hi, r_lo, ctx.ldr, st.xs.hi, st.xs.lo, st.ws.hi, st.ws.lo, st.xs.ld, ptr(st.x), st.x.stride(0),
                 ptr(st.W), st.W.stride(0), row_sum, col_sum, st.xs.aux, st.ws.aux, ptr(g), B, K, D, mode,
@@ -272,7 +274,7 @@ class FusedLossFn(torch.autograd.Function):
             elif ctx.dw_hook is not None:
                 join = ctx.dw_hook(dw)          # data-parallel: start the prototype-gradient all-reduce now
         if ctx.needs_input_grad[0]:
-            dx = torch.empty((B, D), device=dev, dtype=torch.float32)
+            dx = st.dx_out if st.dx_out is not None else torch.empty((B, D), device=dev, dtype=torch.float32)
             check(_gemm("dx", lambda: L.som_backward_dx(r_hi, r_lo, ctx.ldr, st.ws.hi, st.ws.lo, st.ws.ld, ptr(st.x),
                                                         st.x.stride(0), row_sum, st.xs.aux, ptr(g), B, K, D, mode,
                                                         ptr(dx), D, 0, gws, gws_n, stream_ptr())), "som_backward_dx")
