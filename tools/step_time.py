@@ -75,6 +75,8 @@ def main():
     SQUARE = os.environ.get("SOM_GENERAL_GRID") is None
     use_ws = os.environ.get("SOM_NO_WS") is None
     L.som_set_debug(int(os.environ.get("SOM_DEBUG", "0")))
+    if os.environ.get("SOM_BN"):
+        L.som_set_tuning(int(os.environ["SOM_BN"]), 0)          # force the tile width of every GEMM
     wsp, wsn = (gws, gws_n) if use_ws else (None, 0)
 
     def chk(rc, what):

@@ -118,8 +118,10 @@ constexpr int64_t SK_FLAG_WORDS = 4096;      // head of the GEMM workspace: stre
 // L2-bound) but needs enough tiles to keep all 74 pairs busy.  With a workspace the pair kernel can run stream-K:
 // the tiles' k-blocks are spread evenly over the pairs, which removes the tile-count quantisation at the price of
 // one partial-tile round trip through L2 per pair.
-double per_kb_ns(int cg, int bn, double active_sms) {
-  const double gbs_per_sm = std::min(100.0, 10000.0 / active_sms);            // GB/s == bytes/ns
+// MN-major operands arrive as 32 x 32 panels (4 KiB per TMA operation instead of 16 KiB): measured, the chip then
+// delivers ~7.8 TB/s instead of ~10 TB/s (fused backward: 1.09 / 1.24 / 0.93 us per k-block at bn = 192 / 256 / 128).
+double per_kb_ns(int cg, int bn, double active_sms, bool mn_major = false) {
+  const double gbs_per_sm = std::min(100.0, (mn_major ? 7800.0 : 10000.0) / active_sms);   // GB/s == bytes/ns
   const double t_l2 = (128.0 + static_cast<double>(bn) / cg) * 256.0 / gbs_per_sm;
   return std::max(4.43 * bn, t_l2);
 }
@@ -130,13 +132,13 @@ int64_t streamk_workers(int64_t units, int64_t slots, int bn, int64_t ws_floats)
   workers = std::min<int64_t>(workers, SK_FLAG_WORDS / 16);
   return workers >= 2 ? workers : 0;
 }
-double streamk_cost_ns(int64_t units, int64_t workers, int64_t nkb_typ, int bn) {
+double streamk_cost_ns(int64_t units, int64_t workers, int64_t nkb_typ, int bn, bool mn_major) {
   const int64_t per_worker = (units + workers - 1) / workers;
   const double t_epi = 1500.0 + 80.0 * (static_cast<double>(bn) / 2);
   // the pair kernel always has two TMEM buffers: only the last drain of a worker is exposed, the others cost a
   // stall of the issuer when they outlast an accumulation chunk (charged at a quarter)
   const double segs = std::max(1.0, static_cast<double>(per_worker) / static_cast<double>(nkb_typ)) + 1.0;
-  return static_cast<double>(per_worker) * per_kb_ns(2, bn, static_cast<double>(workers) * 2) +
+  return static_cast<double>(per_worker) * per_kb_ns(2, bn, static_cast<double>(workers) * 2, mn_major) +
          t_epi + (segs - 1.0) * t_epi * 0.25 + 4000.0 + 2000.0;
 }
 
@@ -161,7 +163,7 @@ TileChoice pick_tile(int64_t M, int64_t N, int64_t Kred, int sms, int b_mn, int6
     if (forced_sk <= 0 || cg == 1) {
       const int64_t waves = (tiles + slots - 1) / slots;
       const double active_sms = static_cast<double>(tiles < slots ? tiles : slots) * cg;
-      const double t_main = static_cast<double>(nkb) * per_kb_ns(cg, bn, active_sms);
+      const double t_main = static_cast<double>(nkb) * per_kb_ns(cg, bn, active_sms, b_mn != 0);
       const double t_tile = overlap ? std::max(t_main, t_epi) : t_main + t_epi;
       const double cost = static_cast<double>(waves) * t_tile + (overlap ? std::min(t_main, t_epi) : 0.0) + 4000.0;
       if (cost < best_cost - 1e-9) { best_cost = cost; best = TileChoice{cg, bn, 0, 0}; }
@@ -170,7 +172,7 @@ TileChoice pick_tile(int64_t M, int64_t N, int64_t Kred, int sms, int b_mn, int6
       const int64_t units = tiles * nkb;
       const int64_t workers = streamk_workers(units, slots, bn, ws_floats);
       if (workers >= 2 && tiles % workers != 0) {
-        const double cost = streamk_cost_ns(units, workers, nkb, bn);
+        const double cost = streamk_cost_ns(units, workers, nkb, bn, b_mn != 0);
         if (cost < best_cost - 1e-9) { best_cost = cost; best = TileChoice{2, bn, static_cast<int>(workers), 0}; }
       }
       // tile-aligned split-K: fewer tiles than pairs -> every tile cut into `split` equal pieces, one partial-tile
@@ -178,7 +180,7 @@ TileChoice pick_tile(int64_t M, int64_t N, int64_t Kred, int sms, int b_mn, int6
       const int64_t split = tiles > 0 ? std::min<int64_t>(slots / tiles, nkb / 8) : 0;
       if (split >= 2 && tiles * split <= workers) {
         const int64_t piece = (nkb + split - 1) / split;
-        const double cost = static_cast<double>(piece) * per_kb_ns(2, bn, static_cast<double>(tiles * split) * 2) +
+        const double cost = static_cast<double>(piece) * per_kb_ns(2, bn, static_cast<double>(tiles * split) * 2, b_mn != 0) +
                             t_epi + 4000.0 + 2000.0;
         if (cost < best_cost * 1.02) {
           best_cost = std::min(best_cost, cost);
@@ -1254,7 +1256,7 @@ int som_backward_fused(const float* r_hi, const float* r_lo, int64_t ldr, const 
       }
       const int64_t workers = streamk_workers(units, slots, bn, ws_floats);
       if (workers < 2) continue;
-      const double cost = streamk_cost_ns(units, workers, nkb_max, bn);
+      const double cost = streamk_cost_ns(units, workers, nkb_max, bn, true);
       if (cost < best_cost) { best_cost = cost; best_bn = bn; best_workers = workers; }
     }
   }
