@@ -221,7 +221,7 @@ def main():
     ap.add_argument("--row-chunk", type=int, default=0,
                     help="rows per module call (0 = 4096, times the world size when prototypes are sharded)")
     ap.add_argument("--gemm-sms", type=int, default=-1,
-                    help="data parallel: SMs the dx GEMM may occupy while the dW exchange runs (0 = all, -1 = 132)")
+                    help="data parallel: SMs the dx GEMM may occupy while the dW exchange runs (0 = all, -1 = 136)")
     args = ap.parse_args()
     wl = list(WORKLOADS[args.workload])
     if args.distance:
@@ -275,7 +275,7 @@ def main():
     if world > 1 and not sharded:              # batch-sharded DP: prototype-gradient all-reduce over NVLink,
         from vit_som_b200.distributed import DataParallelSOM
         # issued on a side stream from inside backward (runs under the dx GEMM, which leaves 20 SMs to NCCL)
-        gemm_sms = 132 if args.gemm_sms < 0 else args.gemm_sms
+        gemm_sms = 136 if args.gemm_sms < 0 else args.gemm_sms
         dp = DataParallelSOM(layer, gemm_sm_limit=gemm_sms if gemm_sms > 0 else None)
 
     def hot_path(xs):

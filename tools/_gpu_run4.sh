@@ -1,5 +1,5 @@
 set -u
-TAG=${1:-v25}
+TAG=${1:-v29}
 N=${2:-8}
 mkdir -p gpurun_out
 run() { # name, env, args
@@ -15,5 +15,4 @@ PY
   grep -v "OMP_NUM\|\*\*\*\*\|^$" gpurun_out/bench_${TAG}_${name}.err | tail -3
 }
 run c2_n${N}_nvls SOM_DP_NVLS=1 --steps 50 --warmup 5 --no-cpu-baseline
-run c2_n${N}_nccl SOM_DP_NVLS=0 --steps 50 --warmup 5 --no-cpu-baseline
-run c5_n${N} SOM_DP_NVLS=1 --workload cfg5 --steps 5 --warmup 3 --no-cpu-baseline
+run c5_n${N}_nvls SOM_DP_NVLS=1 --workload cfg5 --steps 5 --warmup 3 --no-cpu-baseline

@@ -888,7 +888,9 @@ inline int loss_rows_per_block(int64_t B, int64_t K, int sms) {
 // flag[b][r] in every peer's copy (CAS 0 -> 1, release.sys) and lowers its own copy's flag[b][peer] (CAS 1 -> 0,
 // acquire.sys): self-resetting, so launches (and CUDA-graph replays) can follow each other without host involvement.
 // ----------------------------------------------------------------------------------------------
-constexpr int NVLS_BLOCKS = 32;
+// 16 blocks at two per SM: the kernel fits beside a GEMM that leaves 8+ SMs free (with more blocks than free SMs the
+// late ones would only start after the GEMM, and the exchange would finish after it instead of under it)
+constexpr int NVLS_BLOCKS = 16;
 constexpr int NVLS_UNROLL = 8;
 constexpr int NVLS_THREADS = 512;
 
@@ -919,7 +921,7 @@ __device__ __forceinline__ void nvls_block_barrier(unsigned int* const* flag_ptr
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(NVLS_THREADS)
+__global__ void __launch_bounds__(NVLS_THREADS, 2)
 nvls_allreduce_mean_kernel(float* mc, unsigned int* const* flag_ptrs, long long n4, int rank, int world, float scale) {
   nvls_block_barrier(flag_ptrs, rank, world);            // every rank's dW is complete and visible
   const long long per = (n4 + world - 1) / world;        // float4 elements per rank slice
