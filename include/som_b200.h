@@ -264,7 +264,9 @@ int som_debug_schedule(int64_t tiles0, int64_t nkb0, int64_t tiles1, int64_t nkb
 void som_set_tuning(int bn_override, int kchunk);
 /* Kernel selection: 0 = cost model (default), 1 = single-CTA 128 x bn tiles, 2 = CTA-pair (cta_group::2) 256 x bn tiles. */
 void som_set_cta_group(int cg);
-/* Diagnostics (results are garbage): bit 0 = no TMA loads after the first ring pass, bit 1 = no tensor-core instructions. */
+/* Diagnostics: bit 0 = no TMA loads after the first ring pass, bit 1 = no tensor-core instructions, bit 2 / 3 = gradient
+ * epilogue without src loads / without stores (results are garbage with any of these); bit 4 = one 2-D TMA operation per
+ * MN-major panel instead of one 3-D operation per tile (results unchanged). */
 void som_set_debug(int bits);
 /* Diagnostics: device buffer of 16 uint64 in which CTA 0 of the pair kernel stamps %globaltimer (ns) at its phase
  * boundaries (start, setup done, producer done, issuer done, last accumulators ready, epilogue done, pair synced,

@@ -103,6 +103,26 @@ int make_tmap(CUtensorMap* map, const float* ptr, int64_t inner, int64_t outer, 
   return SOM_OK;
 }
 
+// 3-D view of an MN-major operand stored [Kred rows][mn columns] (row pitch ld): {32 columns of a panel, k, panel}.
+// One TMA operation then brings `panels` 32 x 32 panels of a tile (a 2-D map needs one operation per panel).  Only
+// for mn % 32 == 0: the panel dimension must be exact for out-of-bounds panels to be zero filled.
+int make_tmap_mn3d(CUtensorMap* map, const float* ptr, int64_t mn, int64_t kred, int64_t ld, int panels) {
+  auto enc = get_encode();
+  if (!enc) return fail(SOM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld & 3) != 0 || (mn & 31) != 0)
+    return fail(SOM_ERR_ARG, "3-D TMA operand must be 16-byte aligned, ld % 4 == 0, extent % 32 == 0");
+  cuuint64_t dims[3] = {32u, static_cast<cuuint64_t>(kred), static_cast<cuuint64_t>(mn / 32)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 4, 128u};
+  cuuint32_t box[3] = {32u, 32u, static_cast<cuuint32_t>(panels)};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SOM_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed with CUresult " + std::to_string(r));
+  return SOM_OK;
+}
+std::atomic<int> g_tma3d{1};            // 0 = always one 2-D TMA operation per MN-major panel (diagnostics)
+
 struct TileChoice { int cg; int bn; int sk_workers; int sk_split; };
 
 constexpr int64_t SK_FLAG_WORDS = 4096;      // head of the GEMM workspace: stream-K flags, [worker][16] (<= 256 workers)
@@ -297,6 +317,18 @@ int launch_pair(int epi, const Problem* probs, int nprob, int bn, int sk_workers
     if (int rc = make_problem_maps(probs[i], som::BM, b_rows, &maps[i].a_hi, &maps[i].a_lo, &maps[i].b_hi, &maps[i].b_lo))
       return rc;
     fill_shape(g[i], probs[i], 2, bn, kchunk, passes);
+    // MN-major operands with panel-exact extents: one 3-D TMA operation per tile instead of one per panel
+    const Problem& pr = probs[i];
+    if (g_tma3d.load() && pr.a_mn && pr.M % 32 == 0) {
+      if (int rc = make_tmap_mn3d(&maps[i].a_hi, pr.a_hi, pr.M, pr.Kred, pr.lda, som::BM / 32)) return rc;
+      if (int rc = make_tmap_mn3d(&maps[i].a_lo, pr.a_lo ? pr.a_lo : pr.a_hi, pr.M, pr.Kred, pr.lda, som::BM / 32)) return rc;
+      g[i].a_3d = 1;
+    }
+    if (g_tma3d.load() && pr.b_mn && pr.N % 32 == 0 && b_rows % 32 == 0) {
+      if (int rc = make_tmap_mn3d(&maps[i].b_hi, pr.b_hi, pr.N, pr.Kred, pr.ldb, b_rows / 32)) return rc;
+      if (int rc = make_tmap_mn3d(&maps[i].b_lo, pr.b_lo ? pr.b_lo : pr.b_hi, pr.N, pr.Kred, pr.ldb, b_rows / 32)) return rc;
+      g[i].b_3d = 1;
+    }
     nwork += static_cast<int64_t>(g[i].tiles_m) * g[i].tiles_n;
   }
   if (nprob == 1) { maps[1] = maps[0]; g[1] = g[0]; }
@@ -982,7 +1014,7 @@ void som_set_tuning(int bn_override, int kchunk) {
   g_bn_override.store(bn_override);
   if (kchunk > 0) g_kchunk.store(kchunk);
 }
-void som_set_debug(int bits) { g_debug.store(bits); }
+void som_set_debug(int bits) { g_debug.store(bits & ~16); g_tma3d.store((bits & 16) ? 0 : 1); }
 void som_set_debug_times(unsigned long long* dev_buf) { g_dbg_times.store(dev_buf); }
 void som_set_sm_limit(int max_sms) { g_sm_limit.store(max_sms > 0 ? max_sms : 0); }
 void som_set_streamk(int mode) { g_streamk.store(mode < 0 ? -1 : (mode > 0 ? 1 : 0)); }
