@@ -103,3 +103,22 @@ def test_splitk_pieces_are_tile_aligned(lib):
             assert b[t * split] == t * nkb                        # owner starts at the tile's head
             pieces = [b[t * split + i + 1] - b[t * split + i] for i in range(split)]
             assert sum(pieces) == nkb and pieces[0] == max(pieces)
+
+
+def test_every_worker_of_a_cut_tile_has_work(lib):
+    """Hand-over invariant of the in-kernel reduction: the owner of a cut tile waits for the flag of EVERY worker whose
+    range begins inside the tile, so no such range may be empty (the library only builds schedules with at least 4
+    k-blocks per stream-K worker and at least 8 per split-K piece)."""
+    import random
+    rng = random.Random(1)
+    for _ in range(200):
+        tiles, nkb = rng.randint(1, 200), rng.randint(8, 300)
+        workers = rng.randint(2, min(74, max(2, tiles * nkb // 4)))
+        b = _bounds(lib, tiles, nkb, 0, 0, workers, 0)
+        assert all(y - x >= 4 or tiles * nkb < 4 * workers for x, y in zip(b, b[1:]))
+    for tiles, nkb in [(36, 98), (20, 64), (9, 33), (74, 16), (3, 1000)]:
+        split = min(74 // tiles, nkb // 8)
+        if split < 2:
+            continue
+        b = _bounds(lib, tiles, nkb, 0, 0, tiles * split, split)
+        assert all(y - x >= 1 for x, y in zip(b, b[1:]))
