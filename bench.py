@@ -69,8 +69,17 @@ def workload_config(name, wl, world, chunk, sharded=False):
 
 
 def make_cfg(map_size, D, fcn, Tmax):
-    from oracle.ref_import import make_config
-    return make_config(list(map_size), D, fcn, Tmax=Tmax, Tmin=1e-3)
+    """Config dict in the reference's schema (configs/vit_som/*.yaml; parsed by SOMLayer.__init__,
+    models/som_layer.py:18-40) giving latent_dim = D through the use_reduced branch."""
+    return {
+        "hyperparameters": {
+            "model_arch": "vit_som", "total_epochs": 1, "batch_size": 1,
+            "som": {"map_size": list(map_size), "Tmax": Tmax, "Tmin": 1e-3, "topology": "square",
+                    "distance_fcn": fcn, "use_reduced": True},
+            "vit": {"emb_dim": int(D), "patch_size": 1},
+        },
+        "data": {"input_size": 1},
+    }
 
 
 # ------------------------------------------------------------------------------------------------
