@@ -305,3 +305,24 @@ def test_streamk_forced_matches_oracle(fcn, cuda_device):
     check_against(out, ref.distances, ref.bmu, float(ref.loss), ref.grad_x, ref.grad_w, x, W, fcn, pos, T, 1.0)
     assert out["loss"] == again["loss"] and np.array_equal(out["distances"], again["distances"])
     assert O.rel_err(out["grad_w"], again["grad_w"]) < 5e-7
+
+
+@pytest.mark.parametrize("shape", [(20, (10, 16), 64), (40, (8, 20), 96), (160, (12, 16), 32), (33, (16, 16), 160)])
+def test_pair_kernel_with_short_reductions(shape, cuda_device):
+    """CTA-pair kernel forced on shapes whose reduction dimension is shorter than one k-block or one TMA box
+    (MN-major operands through 3-D tensor maps with k < 32, zero-filled out-of-range panels and k rows)."""
+    from vit_som_b200 import _lib
+    B, ms, D = shape
+    torch.manual_seed(3)
+    layer = make_layer(ms, D, "euclidean", T=2.0)
+    x = torch.randn(B, D).numpy()
+    W = layer.prototypes.detach().cpu().numpy()
+    pos = O.grid_positions(ms)
+    L = _lib.lib()
+    L.som_set_cta_group(2)
+    try:
+        out = run_layer(layer, x)
+    finally:
+        L.som_set_cta_group(0)
+    ref = O.step(x, W, pos, 2.0, "euclidean", 1.0, np.float32)
+    check_against(out, ref.distances, ref.bmu, float(ref.loss), ref.grad_x, ref.grad_w, x, W, "euclidean", pos, 2.0, 1.0)
