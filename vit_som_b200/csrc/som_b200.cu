@@ -138,8 +138,10 @@ constexpr int64_t SK_FLAG_WORDS = 4096;      // head of the GEMM workspace: stre
 // L2-bound) but needs enough tiles to keep all 74 pairs busy.  With a workspace the pair kernel can run stream-K:
 // the tiles' k-blocks are spread evenly over the pairs, which removes the tile-count quantisation at the price of
 // one partial-tile round trip through L2 per pair.
-// MN-major operands arrive as 32 x 32 panels (4 KiB per TMA operation instead of 16 KiB): measured, the chip then
-// delivers ~7.8 TB/s instead of ~10 TB/s (fused backward: 1.09 / 1.24 / 0.93 us per k-block at bn = 192 / 256 / 128).
+// mn_major: MN-major operands that arrive as 32 x 32 panels with one 2-D TMA operation each (4 KiB instead of
+// 16 KiB per operation): measured, the chip then delivers ~7.8 TB/s instead of ~10 TB/s (fused backward: 1.09 / 1.24 /
+// 0.93 us per k-block at bn = 192 / 256 / 128).  Operands whose extent is a multiple of 32 go through 3-D tensor maps
+// (one operation per tile) and pay no penalty: fused backward 109.7 us at bn = 192, 109.3 us at bn = 256.
 double per_kb_ns(int cg, int bn, double active_sms, bool mn_major = false) {
   const double gbs_per_sm = std::min(100.0, (mn_major ? 7800.0 : 10000.0) / active_sms);   // GB/s == bytes/ns
   const double t_l2 = (128.0 + static_cast<double>(bn) / cg) * 256.0 / gbs_per_sm;
@@ -169,7 +171,9 @@ TileChoice pick_tile(int64_t M, int64_t N, int64_t Kred, int sms, int b_mn, int6
   const int64_t nkb = (Kred + som::BK - 1) / som::BK;
   TileChoice best{1, 128, 0, 0};
   double best_cost = 1e300;
+  // MN-major B read panel by panel (no 3-D tensor map: extent not a multiple of 32, single-CTA kernel, or switched off)
   auto consider = [&](int cg, int bn) {
+    const bool panel_loads = b_mn != 0 && (cg == 1 || N % 32 != 0 || (bn / 2) % 32 != 0 || !g_tma3d.load());
     if (forced_cg && cg != forced_cg) return;
     if (forced_bn && bn != forced_bn) return;
     if (cg == 2 && b_mn && (bn / 2) % 32 != 0) return;
@@ -183,7 +187,7 @@ TileChoice pick_tile(int64_t M, int64_t N, int64_t Kred, int sms, int b_mn, int6
     if (forced_sk <= 0 || cg == 1) {
       const int64_t waves = (tiles + slots - 1) / slots;
       const double active_sms = static_cast<double>(tiles < slots ? tiles : slots) * cg;
-      const double t_main = static_cast<double>(nkb) * per_kb_ns(cg, bn, active_sms, b_mn != 0);
+      const double t_main = static_cast<double>(nkb) * per_kb_ns(cg, bn, active_sms, panel_loads);
       const double t_tile = overlap ? std::max(t_main, t_epi) : t_main + t_epi;
       const double cost = static_cast<double>(waves) * t_tile + (overlap ? std::min(t_main, t_epi) : 0.0) + 4000.0;
       if (cost < best_cost - 1e-9) { best_cost = cost; best = TileChoice{cg, bn, 0, 0}; }
@@ -192,7 +196,7 @@ TileChoice pick_tile(int64_t M, int64_t N, int64_t Kred, int sms, int b_mn, int6
       const int64_t units = tiles * nkb;
       const int64_t workers = streamk_workers(units, slots, bn, ws_floats);
       if (workers >= 2 && tiles % workers != 0) {
-        const double cost = streamk_cost_ns(units, workers, nkb, bn, b_mn != 0);
+        const double cost = streamk_cost_ns(units, workers, nkb, bn, panel_loads);
         if (cost < best_cost - 1e-9) { best_cost = cost; best = TileChoice{2, bn, static_cast<int>(workers), 0}; }
       }
       // tile-aligned split-K: fewer tiles than pairs -> every tile cut into `split` equal pieces, one partial-tile
@@ -200,7 +204,7 @@ TileChoice pick_tile(int64_t M, int64_t N, int64_t Kred, int sms, int b_mn, int6
       const int64_t split = tiles > 0 ? std::min<int64_t>(slots / tiles, nkb / 8) : 0;
       if (split >= 2 && tiles * split <= workers) {
         const int64_t piece = (nkb + split - 1) / split;
-        const double cost = static_cast<double>(piece) * per_kb_ns(2, bn, static_cast<double>(tiles * split) * 2, b_mn != 0) +
+        const double cost = static_cast<double>(piece) * per_kb_ns(2, bn, static_cast<double>(tiles * split) * 2, panel_loads) +
                             t_epi + 4000.0 + 2000.0;
         if (cost < best_cost * 1.02) {
           best_cost = std::min(best_cost, cost);
@@ -1290,7 +1294,8 @@ int som_backward_fused(const float* r_hi, const float* r_lo, int64_t ldr, const 
       }
       const int64_t workers = streamk_workers(units, slots, bn, ws_floats);
       if (workers < 2) continue;
-      const double cost = streamk_cost_ns(units, workers, nkb_max, bn, true);
+      const bool panel_loads = D % 32 != 0 || (bn / 2) % 32 != 0 || !g_tma3d.load();    // B of both GEMMs has extent D
+      const double cost = streamk_cost_ns(units, workers, nkb_max, bn, panel_loads);
       if (cost < best_cost) { best_cost = cost; best_bn = bn; best_workers = workers; }
     }
   }
