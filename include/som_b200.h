@@ -22,6 +22,7 @@
  *   som_forward              SOMLayer.forward in one call                 models/som_layer.py:83-89
  *   som_loss_fused           compute_weights + som_loss (+ backward staging) models/som_layer.py:137-152
  *   som_backward_dw/_dx      backward of the fused loss into prototypes / latents
+ *   som_adamw_step           torch.optim.AdamW over som_layer.parameters()   models/vit_som.py:140-151
  *
  * Distance modes: 0 = euclidean (non-squared, ATen `_euclidean_dist` formula
  * sqrt(clamp_min(|x|^2 - 2 x.w + |w|^2, 0))), 1 = cosine (1 - x̂.ŵ with F.normalize eps 1e-12).
@@ -54,9 +55,9 @@ extern "C" {
  * som_gemm_workspace_floats() floats always suffice.
  */
 int64_t som_gemm_workspace_floats(void);
-/* Upper bound on the SMs the tensor-core GEMMs occupy (0 = all).  Data-parallel runs leave a few TPCs to the NCCL
- * kernels of the prototype-gradient all-reduce so that it really runs concurrently with the dx GEMM. */
-void som_set_sm_limit(int max_sms);
+/* Programmatic dependent launch (default on): the kernels of a step are launched so that each may be scheduled while
+ * its predecessor in the stream drains (all of them wait for the predecessor's results before touching memory). */
+void som_set_pdl(int on);
 /* Stream-K policy: -1 never, 0 cost model (default), 1 whenever a workspace is available and the shape allows. */
 void som_set_streamk(int mode);
 
@@ -178,7 +179,11 @@ int som_forward(const float* x, int64_t ldx, const float* W, int64_t ldw,
  * staging of their backward in the same pass over dist[B,K]:
  *   loss_out   = inv_count * sum_{b,k} w[b,k] dist[b,k]              (w recomputed in registers)
  *   R_unit     = inv_count * w / dist (0 where dist == 0) | inv_count * w (cosine), tf32 hi/lo split
- *   row_sum[b] = sum_k R_unit | sum_k R_unit (1 - dist);   col_sum[k] likewise over b
+ *   row_part [B, n_row_parts]  : partial sums over 128-column slabs of  R_unit | R_unit (1 - dist)
+ *   col_part [n_col_parts, K]  : partial sums over row blocks of the same terms
+ * (n_row_parts / n_col_parts from som_loss_fused_parts).  The partial sums are plain stores - no atomics, no
+ * zero-initialisation - and the gradient GEMMs add the parts of a row in index order, so gradients are run-to-run
+ * bit-identical; the loss is reduced in a fixed order in fp64.
  * grid_rows / grid_cols > 0 declare that grid_pos is the canonical square grid (cell k at (k / cols, k % cols),
  * models/som_layer.py:61-67); the weight is then evaluated in its factorised form e[|dr|] * e[|dc|] from a small
  * table (a few ulp from the reference's exp(-(sqrt(dr^2+dc^2))^2 / 2T^2)).  Pass 0, 0 for any other grid (hexa).
@@ -186,45 +191,71 @@ int som_forward(const float* x, int64_t ldx, const float* W, int64_t ldw,
  * scratch: at least som_loss_fused_scratch_floats(B, K) floats, word 0 zero on entry (restored on exit).
  */
 int64_t som_loss_fused_scratch_floats(int64_t B, int64_t K);
+int som_loss_fused_parts(int64_t B, int64_t K, int64_t* n_row_parts, int64_t* n_col_parts);
 int som_loss_fused(const float* dist, int64_t ldd, const int64_t* bmu, const float* grid_pos,
                    int grid_rows, int grid_cols,
                    int64_t B, int64_t K, int64_t k_offset, const float* T_dev, float inv_count, int mode,
-                   float* r_hi, float* r_lo, int64_t ldr, float* row_sum, float* col_sum,
+                   float* r_hi, float* r_lo, int64_t ldr, float* row_part, float* col_part,
                    float* scratch, float* loss_out, void* stream);
 
 /*
  * The two gradient GEMMs of the closed-form backward (ATen _euclidean_dist_backward | MmBackward0 +
  * normalize backward), with g = *g_dev the upstream gradient of the loss:
- *   dW[k,:] (+)= g * (c_k W[k,:] - s_k sum_b R_unit[b,k] x~[b,:])     c, s from col_sum / w_aux
- *   dx[b,:] (+)= g * (c_b x[b,:] - s_b sum_k R_unit[b,k] W~[k,:])     c, s from row_sum / x_aux
- * euclidean: c = sum, s = 1;  cosine: c = aux^2 * sum, s = aux.  accumulate != 0 adds into the output
- * (row-chunked batches accumulate dW across chunks).
+ *   dW[k,:] (+)= g * (c_k W[k,:] - s_k sum_b R_unit[b,k] x~[b,:])     c, s from col_part / w_aux
+ *   dx[b,:] (+)= g * (c_b x[b,:] - s_b sum_k R_unit[b,k] W~[k,:])     c, s from row_part / x_aux
+ * euclidean: c = sum of the row's parts, s = 1;  cosine: c = aux^2 * sum, s = aux.  accumulate != 0 adds into the
+ * output (row-chunked batches accumulate dW across chunks).  sm_limit > 0: the launch occupies at most that many SMs
+ * (the caller runs a collective kernel beside it); 0 = all.
  */
 int som_backward_dw(const float* r_hi, const float* r_lo, int64_t ldr,
                     const float* x_hi, const float* x_lo, int64_t ld_stage,
-                    const float* W, int64_t ldw, const float* col_sum, const float* w_aux,
+                    const float* W, int64_t ldw, const float* col_part, int64_t n_col_parts, const float* w_aux,
                     const float* g_dev, int64_t B, int64_t K, int64_t D, int mode,
-                    float* dW, int64_t lddw, int accumulate,
+                    float* dW, int64_t lddw, int accumulate, int sm_limit,
                     float* ws, int64_t ws_floats, void* stream);
 int som_backward_dx(const float* r_hi, const float* r_lo, int64_t ldr,
                     const float* w_hi, const float* w_lo, int64_t ld_stage,
-                    const float* x, int64_t ldx, const float* row_sum, const float* x_aux,
+                    const float* x, int64_t ldx, const float* row_part, int64_t n_row_parts, const float* x_aux,
                     const float* g_dev, int64_t B, int64_t K, int64_t D, int mode,
-                    float* dx, int64_t lddx, int accumulate,
+                    float* dx, int64_t lddx, int accumulate, int sm_limit,
                     float* ws, int64_t ws_floats, void* stream);
 
 /*
- * Both gradient GEMMs above in ONE persistent CTA-pair launch (their tiles share one stream-K work list): same
- * results as som_backward_dw followed by som_backward_dx, one prologue / tail instead of two.  Needs the GEMM
- * workspace; without it (or for tiny shapes) it issues the two launches.
+ * Both gradient GEMMs above in ONE persistent CTA-pair launch (their tiles share one stream-K work list, dW tiles
+ * first): same results as som_backward_dw followed by som_backward_dx, one prologue / tail instead of two.  Needs the
+ * GEMM workspace; without it (or for tiny shapes) it issues the two launches.
+ * Data parallel: dw_done != NULL -> every finished 32-row slab of dW adds 1 to *dw_done (a zero-initialised device
+ * word) and *dw_done_expected (host) receives the final count, so the exchange of dW can start from another stream
+ * behind som_stream_wait_value(dw_done, expected) while the dx tiles are still running; -1 = not counted (fallback
+ * launches: order the exchange after this call).
  */
 int som_backward_fused(const float* r_hi, const float* r_lo, int64_t ldr,
                        const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo, int64_t ld_stage,
                        const float* x, int64_t ldx, const float* W, int64_t ldw,
-                       const float* row_sum, const float* col_sum, const float* x_aux, const float* w_aux,
+                       const float* row_part, int64_t n_row_parts, const float* col_part, int64_t n_col_parts,
+                       const float* x_aux, const float* w_aux,
                        const float* g_dev, int64_t B, int64_t K, int64_t D, int mode,
                        float* dW, int64_t lddw, int accumulate_dw, float* dx, int64_t lddx,
+                       int sm_limit, unsigned int* dw_done, int64_t* dw_done_expected,
                        float* ws, int64_t ws_floats, void* stream);
+
+/* Stream-ordered memory operations (cuStreamWaitValue32 GEQ / cuStreamWriteValue32): `stream` proceeds once
+ * *addr >= value; executed by the GPU front end (no SM is occupied while waiting), capturable in CUDA graphs. */
+int som_stream_wait_value(unsigned int* addr, unsigned int value, void* stream);
+int som_stream_write_value(unsigned int* addr, unsigned int value, void* stream);
+
+/*
+ * Prototype optimizer step fused with the operand staging of the next forward (the reference optimises
+ * som_layer.parameters() with torch.optim.AdamW, models/vit_som.py:140-151): one pass that reads W, dW, m, v and
+ * writes W, m, v AND, when w_hi != NULL, the staging of the new prototypes (tf32 hi/lo split + |w|^2 or 1/max(|w|,
+ * 1e-12), exactly what som_prep_rows produces), so the next som_forward runs with stage_w = 0.
+ *   hp_dev: device float[3] = {lr, t, grad_scale}: learning rate, 1-based step count, factor applied to dW
+ *   beta1, beta2, eps, weight_decay: as torch.optim.AdamW (decoupled decay, bias-corrected moments, no amsgrad)
+ */
+int som_adamw_step(float* W, int64_t ldw, const float* dW, int64_t lddw, float* m, float* v, int64_t ldm,
+                   int64_t K, int64_t D, const float* hp_dev, double beta1, double beta2, double eps,
+                   double weight_decay, int mode, float* w_hi, float* w_lo, int64_t ld_stage, float* w_aux,
+                   void* stream);
 
 /*
  * Exchange step of batch-sharded data parallelism (the reference gets it from Lightning DDP's bucketed NCCL

@@ -11,16 +11,38 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "som_b200.h")
 
 
-def declared_functions():
-    """{name: number of parameters} parsed from the header (comments stripped)."""
-    src = open(HEADER).read()
+def _strip_comments(src):
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    src = re.sub(r"//[^\n]*", "", src)
+    return re.sub(r"//[^\n]*", "", src)
+
+
+def declared_prototypes():
+    """{name: [C type of every parameter]} parsed from the header (comments stripped, parameter names dropped)."""
+    src = _strip_comments(open(HEADER).read())
     out = {}
     for m in re.finditer(r"\b(?:int|int64_t|void|const char\*)\s+(som_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
         name, params = m.group(1), m.group(2).strip()
-        out[name] = 0 if params in ("", "void") else params.count(",") + 1
+        types = []
+        if params not in ("", "void"):
+            for prm in params.split(","):
+                prm = " ".join(prm.split())
+                t = re.sub(r"\s*\b\w+$", "", prm) if not prm.endswith("*") else prm      # drop the parameter name
+                types.append(t.replace(" *", "*"))
+        out[name] = types
     return out
+
+
+def declared_functions():
+    """{name: number of parameters}."""
+    return {k: len(v) for k, v in declared_prototypes().items()}
+
+
+def ctype_of(c_type):
+    """The ctypes type a C parameter type must be bound with (every pointer travels as void*)."""
+    if c_type.endswith("*"):
+        return ctypes.c_void_p
+    return {"int": ctypes.c_int, "int64_t": ctypes.c_int64, "float": ctypes.c_float, "double": ctypes.c_double,
+            "unsigned int": ctypes.c_uint32}[c_type]
 
 
 @pytest.fixture(scope="module")
@@ -42,9 +64,58 @@ def test_header_symbols_are_exported_and_bound(lib):
         assert name in decl, f"{name} is bound in _lib.py but not declared in include/som_b200.h"
 
 
+def test_ctypes_signatures_match_the_header_type_for_type():
+    """Every argument of every binding has the ctypes type of the header's parameter at that position (an int where
+    the header has an int64_t - or two swapped arguments of different types - would corrupt the call silently)."""
+    from vit_som_b200 import _lib
+    for name, c_types in declared_prototypes().items():
+        bound = _lib.SIGNATURES[name][1]
+        for i, (c_t, b) in enumerate(zip(c_types, bound)):
+            assert ctype_of(c_t) is b, f"{name} argument {i}: header `{c_t}` but bound as {b.__name__}"
+
+
+def _integration_md():
+    return open(os.path.join(ROOT, "INTEGRATION.md")).read()
+
+
+def test_integration_doc_ctypes_stub_matches_the_header():
+    """The ctypes stub printed in INTEGRATION.md declares som_forward with the header's parameter list (the round-1
+    document had lost two parameters: a maintainer who followed it passed the stream where the workspace goes)."""
+    md = _integration_md()
+    m = re.search(r"L\.som_forward\.argtypes\s*=\s*\[(.*?)\]", md, flags=re.S)
+    assert m, "INTEGRATION.md no longer shows the som_forward ctypes stub"
+    body = re.sub(r"#[^\n]*", "", m.group(1))
+    names = [t.strip() for t in body.replace("\n", " ").split(",") if t.strip()]
+    alias = {"P": ctypes.c_void_p, "I64": ctypes.c_int64, "I": ctypes.c_int, "F": ctypes.c_float}
+    doc_types = [alias[n] for n in names]
+    header_types = [ctype_of(t) for t in declared_prototypes()["som_forward"]]
+    assert doc_types == header_types
+    # the call in the stub passes as many arguments as the header has parameters
+    call = re.search(r"rc = L\.som_forward\((.*?)\)\n\s*if rc", md, flags=re.S)
+    assert call
+    depth, nargs = 0, 1
+    for ch in call.group(1):
+        depth += ch in "([" 
+        depth -= ch in ")]"
+        nargs += ch == "," and depth == 0
+    assert nargs == len(header_types)
+
+
+def test_integration_doc_cpp_stub_matches_the_header():
+    md = _integration_md()
+    call = re.search(r"int rc = som_forward\((.*?)\);\n", md, flags=re.S)
+    assert call, "INTEGRATION.md no longer shows the libtorch stub"
+    depth, nargs = 0, 1
+    for ch in call.group(1):
+        depth += ch in "(<"
+        depth -= ch in ")>"
+        nargs += ch == "," and depth == 0
+    assert nargs == len(declared_prototypes()["som_forward"])
+
+
 def test_abi_version_and_pure_host_entry_points(lib):
-    assert lib.som_b200_abi_version() == 5
-    assert lib.som_gemm_workspace_floats() == 4096 + 74 * 256 * 256
+    assert lib.som_b200_abi_version() == 6
+    assert lib.som_gemm_workspace_floats() == 4096 + 74 * 256 * 256      # 74 CTA pairs: a B200, and the GPU-less default
     assert lib.som_loss_scratch_floats(1024, 1600) >= 1024 * 2
     assert lib.som_loss_fused_scratch_floats(1024, 1600) == (1024 // 8) * 4 + 2
     lib.som_launch_count_reset()

@@ -8,6 +8,8 @@ The numeric work lives in ``libsom_b200.so`` (C ABI: include/som_b200.h); build 
 from ._lib import SomError, build, lib  # noqa: F401
 from .glue import gamma_ramp, som_input  # noqa: F401
 from .graph import StepGraph  # noqa: F401
+from .optim import FusedPrototypeAdamW  # noqa: F401
 from .som_layer import NeighbourhoodWeights, SOMLayer  # noqa: F401
 
-__all__ = ["SOMLayer", "NeighbourhoodWeights", "StepGraph", "gamma_ramp", "som_input", "SomError", "build", "lib"]
+__all__ = ["SOMLayer", "NeighbourhoodWeights", "FusedPrototypeAdamW", "StepGraph", "gamma_ramp", "som_input", "SomError",
+           "build", "lib"]

@@ -11,7 +11,7 @@ import os
 import shutil
 import subprocess
 import threading
-from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_uint32, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
@@ -41,7 +41,7 @@ SIGNATURES = {
                                   c_int64, _P, c_int64, _P, _P, c_int64, _P]),
     "som_gemm_workspace_floats": (c_int64, []),
     "som_set_streamk": (None, [c_int]),
-    "som_set_sm_limit": (None, [c_int]),
+    "som_set_pdl": (None, [c_int]),
     "som_bmu_decode": (c_int, [_P, c_int64, c_int64, _P, _P, _P]),
     "som_neighbourhood": (c_int, [_P, _P, c_int64, c_int64, c_int64, _P, _P, c_int64, _P]),
     "som_loss_scratch_floats": (c_int64, [c_int64, c_int64]),
@@ -56,15 +56,20 @@ SIGNATURES = {
     "som_forward": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int64,
                             _P, _P, _P, _P, _P, _P, c_int64, _P, c_int64, _P, _P, c_int64, _P, c_int64, _P]),
     "som_loss_fused_scratch_floats": (c_int64, [c_int64, c_int64]),
+    "som_loss_fused_parts": (c_int, [c_int64, c_int64, _P, _P]),
     "som_loss_fused": (c_int, [_P, c_int64, _P, _P, c_int, c_int, c_int64, c_int64, c_int64, _P, c_float, c_int,
                                _P, _P, c_int64, _P, _P, _P, _P, _P]),
-    "som_backward_dw": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, c_int64, _P, _P, _P,
-                                c_int64, c_int64, c_int64, c_int, _P, c_int64, c_int, _P, c_int64, _P]),
-    "som_backward_dx": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, c_int64, _P, _P, _P,
-                                c_int64, c_int64, c_int64, c_int, _P, c_int64, c_int, _P, c_int64, _P]),
-    "som_backward_fused": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, c_int64, _P, c_int64, _P, c_int64, _P, _P, _P, _P,
-                                   _P, c_int64, c_int64, c_int64, c_int, _P, c_int64, c_int, _P, c_int64,
-                                   _P, c_int64, _P]),
+    "som_backward_dw": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, c_int64, _P, c_int64, _P, _P,
+                                c_int64, c_int64, c_int64, c_int, _P, c_int64, c_int, c_int, _P, c_int64, _P]),
+    "som_backward_dx": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, c_int64, _P, c_int64, _P, _P,
+                                c_int64, c_int64, c_int64, c_int, _P, c_int64, c_int, c_int, _P, c_int64, _P]),
+    "som_backward_fused": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, c_int64, _P, c_int64, _P, c_int64,
+                                   _P, c_int64, _P, c_int64, _P, _P, _P, c_int64, c_int64, c_int64, c_int,
+                                   _P, c_int64, c_int, _P, c_int64, c_int, _P, _P, _P, c_int64, _P]),
+    "som_stream_wait_value": (c_int, [_P, c_uint32, _P]),
+    "som_stream_write_value": (c_int, [_P, c_uint32, _P]),
+    "som_adamw_step": (c_int, [_P, c_int64, _P, c_int64, _P, _P, c_int64, c_int64, c_int64, _P, c_double, c_double,
+                               c_double, c_double, c_int, _P, _P, c_int64, _P, _P]),
     "som_allreduce_mean_nvls": (c_int, [_P, _P, c_int64, c_int, c_int, _P]),
     "som_allreduce_nvls": (c_int, [_P, _P, c_int64, c_int, c_int, c_float, _P]),
     "som_nvls_flag_words": (c_int64, [c_int]),
@@ -140,6 +145,7 @@ def ptr(t) -> int | None:
     return None if t is None else t.data_ptr()
 
 
-def stream_ptr() -> int:
+def stream_ptr(device=None) -> int:
+    """Raw handle of the current CUDA stream of ``device`` (default: the current device)."""
     import torch
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream(device).cuda_stream

@@ -31,7 +31,7 @@ std::atomic<int> g_debug{0};            // GemmShape::debug (diagnostic runs of 
 std::atomic<int> g_cg_override{0};
 std::atomic<unsigned long long*> g_dbg_times{nullptr};
 std::atomic<int> g_streamk{0};          // -1 = never, 0 = cost model, 1 = whenever possible
-std::atomic<int> g_sm_limit{0};         // 0 = all SMs; otherwise the GEMMs use at most this many (rest left to collectives)      // 0 = cost model, 1 = single-CTA kernel, 2 = CTA-pair kernel
+std::atomic<int> g_pdl{1};              // 1 = launch with programmatic stream serialization (kernel prologues overlap the predecessor's tail)
 
 int fail(int code, const std::string& msg) {
   g_last_error = msg;
@@ -44,7 +44,22 @@ int fail(int code, const std::string& msg) {
       return fail(SOM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__));             \
   } while (0)
 
-struct DeviceInfo { int sms = 0; int cc_major = 0; bool ok = false; };
+struct DeviceInfo { int sms = 0; int cc_major = 0; int dev = 0; bool ok = false; };
+
+// Every kernel of the step is launched through this helper: with the programmatic-stream-serialization attribute the
+// kernel may be scheduled while its predecessor in the stream drains; all kernels of this library execute
+// griddepcontrol.wait before they touch global memory, so results are unchanged (som_set_pdl(0) switches it off).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl.load() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
+}
 
 int device_info(DeviceInfo& out) {
   static thread_local int cached_dev = -1;
@@ -60,6 +75,7 @@ int device_info(DeviceInfo& out) {
     SOM_CUDA(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
     SOM_CUDA(cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
     d.ok = true;
+    d.dev = dev;
     cached = d;
     cached_dev = dev;
   }
@@ -265,18 +281,23 @@ void fill_shape(som::GemmShape& g, const Problem& p, int cg, int bn, int kchunk,
   g.tiles_n = static_cast<int>((p.N + bn - 1) / bn);
 }
 
+constexpr int kMaxDevices = 64;
+
 template <int EPI>
 int launch_single_t(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi,
                     const CUtensorMap& tb_lo, const som::GemmShape& g, const som::EpiParams& e, int grid, size_t smem,
                     cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<bool> attr_set[kMaxDevices];        // the attribute is per device (and per kernel instance)
+  int dev = 0;
+  SOM_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices) return fail(SOM_ERR_DEVICE, "device ordinal out of range");
+  if (!attr_set[dev].load(std::memory_order_acquire)) {
     SOM_CUDA(cudaFuncSetAttribute(som::som_gemm3x_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   som::SMEM_LIMIT));
-    attr_set = true;
+    attr_set[dev].store(true, std::memory_order_release);
   }
-  som::som_gemm3x_kernel<EPI><<<grid, som::NUM_THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, g, e);
-  SOM_CUDA(cudaGetLastError());
+  SOM_CUDA(launch_kernel(som::som_gemm3x_kernel<EPI>, dim3(grid), dim3(som::NUM_THREADS), smem, st, ta_hi, ta_lo, tb_hi,
+                         tb_lo, g, e));
   g_launches.fetch_add(1);
   return SOM_OK;
 }
@@ -284,14 +305,17 @@ int launch_single_t(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CU
 template <int EPI>
 int launch_pair_t(const som::PairMaps& m0, const som::PairMaps& m1, const som::GemmShape& g0, const som::EpiParams& e0,
                   const som::GemmShape& g1, const som::EpiParams& e1, int grid, size_t smem, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<bool> attr_set[kMaxDevices];
+  int dev = 0;
+  SOM_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices) return fail(SOM_ERR_DEVICE, "device ordinal out of range");
+  if (!attr_set[dev].load(std::memory_order_acquire)) {
     SOM_CUDA(cudaFuncSetAttribute(som::som_gemm3x_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   som::SMEM_LIMIT));
-    attr_set = true;
+    attr_set[dev].store(true, std::memory_order_release);
   }
-  som::som_gemm3x_pair_kernel<EPI><<<grid, som::NUM_THREADS_2CTA, smem, st>>>(m0, m1, g0, e0, g1, e1);
-  SOM_CUDA(cudaGetLastError());
+  SOM_CUDA(launch_kernel(som::som_gemm3x_pair_kernel<EPI>, dim3(grid), dim3(som::NUM_THREADS_2CTA), smem, st, m0, m1, g0,
+                         e0, g1, e1));
   g_launches.fetch_add(1);
   return SOM_OK;
 }
@@ -364,20 +388,22 @@ int launch_pair(int epi, const Problem* probs, int nprob, int bn, int sk_workers
   return fail(SOM_ERR_ARG, "unknown epilogue");
 }
 
-int effective_sms(int* sms) {
+// SMs a GEMM launch may occupy: all of them, or at most `sm_limit` (whole TPC pairs) when the caller runs a collective
+// kernel beside it (a per-call argument: nothing process-wide is involved).
+int effective_sms(int* sms, int sm_limit = 0) {
   DeviceInfo di;
   if (int rc = device_info(di)) return rc;
-  const int sm_limit = g_sm_limit.load();
-  if (sm_limit >= 2 && sm_limit < di.sms) di.sms = sm_limit & ~1;      // leave SMs (whole TPC pairs) to a concurrent collective
+  if (sm_limit >= 2 && sm_limit < di.sms) di.sms = sm_limit & ~1;
   *sms = di.sms;
   return SOM_OK;
 }
 
 int launch_gemm(int epi, const float* a_hi, const float* a_lo, int64_t lda, int a_mn, const float* b_hi,
                 const float* b_lo, int64_t ldb, int b_mn, int64_t M, int64_t N, int64_t Kred, int bn_req,
-                int kchunk_req, int passes, const som::EpiParams& e, float* ws, int64_t ws_floats, cudaStream_t st) {
+                int kchunk_req, int passes, const som::EpiParams& e, float* ws, int64_t ws_floats, cudaStream_t st,
+                int sm_limit = 0) {
   int sms = 0;
-  if (int rc = effective_sms(&sms)) return rc;
+  if (int rc = effective_sms(&sms, sm_limit)) return rc;
   if (passes != 1 && passes != 3) return fail(SOM_ERR_ARG, "passes must be 1 or 3");
   if (ws && (reinterpret_cast<uintptr_t>(ws) & 15) != 0) return fail(SOM_ERR_ARG, "workspace must be 16-byte aligned");
   Problem p{a_hi, a_lo, lda, a_mn, b_hi, b_lo, ldb, b_mn, M, N, Kred, e};
@@ -436,6 +462,8 @@ struct PrepSet {
 template <int GROUP>
 __global__ void __launch_bounds__(256)
 prep_rows_kernel(const PrepSet sa, const PrepSet sb, long long blocks_a, int dim, int mode, long long ld_out) {
+  som::pdl_wait();
+  som::pdl_launch_dependents();
   constexpr int ROWS_PER_BLOCK = 256 / GROUP;
   const int gi = threadIdx.x / GROUP, gt = threadIdx.x % GROUP;
   const bool second = static_cast<long long>(blockIdx.x) >= blocks_a;
@@ -534,12 +562,16 @@ prep_rows_kernel(const PrepSet sa, const PrepSet sb, long long blocks_a, int dim
 }
 
 __global__ void bmu_init_kernel(long long* packed, long long n) {
+  som::pdl_wait();
+  som::pdl_launch_dependents();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) packed[i] = 0x7fffffffffffffffLL;
 }
 
 __global__ void bmu_decode_kernel(const long long* __restrict__ packed, long long n, long long k_total,
                                   long long* __restrict__ bmu, float* __restrict__ min_key) {
+  som::pdl_wait();
+  som::pdl_launch_dependents();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const long long p = packed[i];
@@ -566,6 +598,8 @@ constexpr int COLS_PER_BLOCK = 1024;   // 256 threads x 4 columns
 __global__ void __launch_bounds__(256)
 neighbourhood_kernel(const long long* __restrict__ bmu, const float* __restrict__ pos, long long K, long long k_offset,
                      const float* __restrict__ T_dev, float* __restrict__ w, long long ldw) {
+  som::pdl_wait();
+  som::pdl_launch_dependents();
   const long long b = blockIdx.x;
   const float T = __ldg(T_dev);
   const float two_t2 = 2.f * (T * T);
@@ -584,6 +618,8 @@ __global__ void __launch_bounds__(256)
 weighted_loss_kernel(const float* __restrict__ dist, long long ldd, const long long* __restrict__ bmu,
                      const float* __restrict__ pos, long long K, long long k_offset, const float* __restrict__ T_dev,
                      float inv_count, float* __restrict__ partials, float* __restrict__ loss_out) {
+  som::pdl_wait();
+  som::pdl_launch_dependents();
   const long long b = blockIdx.x;
   const float T = __ldg(T_dev);
   const float two_t2 = 2.f * (T * T);
@@ -639,6 +675,8 @@ __global__ void __launch_bounds__(256)
 loss_grad_kernel(const long long* __restrict__ bmu, const float* __restrict__ pos, long long K, long long k_offset,
                  const float* __restrict__ T_dev, const float* __restrict__ g_out, float inv_count,
                  float* __restrict__ G, long long ldg) {
+  som::pdl_wait();
+  som::pdl_launch_dependents();
   const long long b = blockIdx.x;
   const float T = __ldg(T_dev);
   const float two_t2 = 2.f * (T * T);
@@ -663,6 +701,8 @@ bwd_coeffs_kernel(const float* __restrict__ G, long long ldg, const float* __res
                   long long B, long long K, int mode, const float* __restrict__ x_aux, const float* __restrict__ w_aux,
                   float* __restrict__ r_hi, float* __restrict__ r_lo, long long ldr,
                   float* __restrict__ ax, float* __restrict__ bx, float* __restrict__ aw, float* __restrict__ bw) {
+  som::pdl_wait();
+  som::pdl_launch_dependents();
   const long long k = static_cast<long long>(blockIdx.y) * 256 + threadIdx.x;
   const long long b0 = static_cast<long long>(blockIdx.x) * COEFF_ROWS;
   const bool col_ok = k < K;
@@ -715,21 +755,25 @@ bwd_coeffs_kernel(const float* __restrict__ G, long long ldg, const float* __res
 // distance-backward chain): one pass over dist[B,K] produces
 //   * the loss  inv_count * sum w d  (w recomputed in registers, never stored),
 //   * R_unit = dL/dd / d for unit upstream gradient, as the tf32 hi/lo GEMM operand, and
-//   * its row / column sums (the rank-1 coefficients of the closed-form backward).
+//   * partial row / column sums of it (the rank-1 coefficients of the closed-form backward).
 // The upstream gradient g_out multiplies the result in the epilogue of the gradient GEMMs, so backward needs no
 // further pass over B x K.  r_hi == nullptr: loss only (validation / no_grad).
-// Block = 8 rows x 512 columns: warp (rh, cs) owns 4 rows x 128 columns, a lane 4 consecutive columns (one
-// 16-byte load of dist, two 16-byte stores of R per row); row sums by warp shuffle, column sums in registers, the
-// two row halves of a block combined in shared memory before the one atomicAdd per column.  The kernel is bound
-// by instruction latency (ncu: IPC 0.28 per scheduler at 14 warps/SM), hence the small blocks (27 warps/SM).
+// Block = rows_per_block rows x 512 columns: warp (rh, cs) owns half of the rows x 128 columns, a lane 4 consecutive
+// columns (one 16-byte load of dist, two 16-byte stores of R per row; the loads of the next 4 rows are issued before
+// the current 4 are processed).
+// Everything is deterministic (run-to-run bit-identical): no atomics.  A warp writes the sum of its 128 columns of a
+// row to row_part[b][slab] (slab = global 128-column slab), a block writes its column sums (the two row halves added
+// in shared memory, fixed order) to col_part[row block][k]; the gradient GEMM epilogues add the partial sums of a
+// row in index order (som_gemm.cuh grad_coeffs).  The loss: per-block partial, the last block to finish adds all
+// partials in fp64 in a fixed order - only its first warp stays for that, nobody waits at a block barrier behind
+// the completion counter.
 constexpr int LC_ROWS = 8;
 constexpr int LC_COLS = 512;
 
 // SQUARE: the map is the canonical integer grid of the square topology (models/som_layer.py:61-67), cell k at
 // (k / cols, k % cols).  Then the neighbourhood weight factorises, exp(-(dr^2 + dc^2) / 2T^2) = e[|dr|] * e[|dc|], and
-// a block needs max(rows, cols) exponentials in shared memory instead of one per element (the kernel is bound by
-// instruction issue: ~110 instructions per element on the general path, ~30 here).  The factorised weight differs
-// from the reference's exp(-(sqrt(dr^2 + dc^2))^2 / 2T^2) by a few ulp (1e-7 relative), inside the 1e-5 budget.
+// a block needs max(rows, cols) exponentials in shared memory instead of one per element.  The factorised weight
+// differs from the reference's exp(-(sqrt(dr^2 + dc^2))^2 / 2T^2) by a few ulp (1e-7 relative), inside the 1e-5 budget.
 constexpr int LC_MAX_TAB = 1024;
 
 template <bool SQUARE>
@@ -738,21 +782,22 @@ loss_coeffs_kernel(const float* __restrict__ dist, long long ldd, const long lon
                    const float* __restrict__ pos, int grid_rows, int grid_cols, long long B, long long K,
                    long long k_offset, const float* __restrict__ T_dev, float inv_count, int mode,
                    float* __restrict__ r_hi, float* __restrict__ r_lo, long long ldr,
-                   float* __restrict__ row_sum, float* __restrict__ col_sum,
+                   float* __restrict__ row_part, int n_row_parts, float* __restrict__ col_part,
                    float* __restrict__ partials, float* __restrict__ loss_out, int rows_per_block) {
+  som::pdl_wait();
+  som::pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rh = warp >> 2, cs = warp & 3;
   const int half_rows = rows_per_block >> 1;              // rows handled by each of the two warp rows (multiple of 4)
   const long long k0 = static_cast<long long>(blockIdx.y) * LC_COLS + cs * 128 + lane * 4;
   const long long b_base = static_cast<long long>(blockIdx.x) * rows_per_block + rh * half_rows;
+  const int slab = static_cast<int>(blockIdx.y) * 4 + cs;     // global 128-column slab of this warp
   const bool want_r = r_hi != nullptr;
   const bool vec = (ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(dist) & 15) == 0 &&
                    (!want_r || ((ldr & 3) == 0 && ((reinterpret_cast<uintptr_t>(r_hi) | reinterpret_cast<uintptr_t>(r_lo)) & 15) == 0));
   __shared__ float lred[8];
   __shared__ float csum[LC_COLS];
   __shared__ float tab[SQUARE ? LC_MAX_TAB : 1];
-  __shared__ double dred[256];
-  __shared__ bool is_last;
 
   const float T = __ldg(T_dev);
   const float two_t2 = 2.f * (T * T);
@@ -787,12 +832,38 @@ loss_coeffs_kernel(const float* __restrict__ dist, long long ldd, const long lon
     }
     __syncthreads();
   }
+  // the 4 distances of row b in this lane's columns
+  auto load_dist = [&](long long b, float (&d)[4]) {
+    d[0] = d[1] = d[2] = d[3] = 0.f;
+    if (b < B && ok[0]) {
+      if (vec) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(dist + b * ldd + k0));
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if (ok[i]) d[i] = __ldg(dist + b * ldd + k0 + i);
+      }
+    }
+  };
   float colsum[4] = {0.f, 0.f, 0.f, 0.f};
   float lsum = 0.f;
+  float dn[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) load_dist(b_base + r, dn[r]);
   for (int r4 = 0; r4 < half_rows; r4 += 4) {
     const long long b0 = b_base + r4;
     if (b0 >= B) break;                                    // warp-uniform
-    // BMU grid position of the next 4 rows: lane r loads row r, broadcast by shuffle below
+    float dc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dc[r][i] = dn[r][i];
+    }
+    if (r4 + 4 < half_rows) {                              // next group's distances: in flight while this one is processed
+#pragma unroll
+      for (int r = 0; r < 4; ++r) load_dist(b0 + 4 + r, dn[r]);
+    }
+    // BMU grid position of these 4 rows: lane r loads row r, broadcast by shuffle below
     float2 pbv = make_float2(0.f, 0.f);
     int rbv = 0, cbv = 0;
     if (lane < 4 && b0 + lane < B) {
@@ -811,16 +882,7 @@ loss_coeffs_kernel(const float* __restrict__ dist, long long ldd, const long lon
       const float pby = __shfl_sync(0xffffffffu, pbv.x, r), pbx = __shfl_sync(0xffffffffu, pbv.y, r);
       const int rb = __shfl_sync(0xffffffffu, rbv, r), cb = __shfl_sync(0xffffffffu, cbv, r);
       if (b >= B) break;                                   // warp-uniform
-      float d[4] = {0.f, 0.f, 0.f, 0.f};
-      if (ok[0]) {
-        if (vec) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(dist + b * ldd + k0));
-          d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-        } else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) if (ok[i]) d[i] = __ldg(dist + b * ldd + k0 + i);
-        }
-      }
+      const float (&d)[4] = dc[r];
       float h[4], l[4], rowterm = 0.f;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -857,8 +919,8 @@ loss_coeffs_kernel(const float* __restrict__ dist, long long ldd, const long lon
             for (int i = 0; i < 4; ++i) if (ok[i]) { r_hi[b * ldr + k0 + i] = h[i]; r_lo[b * ldr + k0 + i] = l[i]; }
           }
         }
-        rowterm = warp_sum(rowterm);
-        if (lane == 0) atomicAdd(row_sum + b, rowterm);
+        rowterm = warp_sum(rowterm);                       // xor butterfly: the same value, bit for bit, in every run
+        if (lane == 0 && slab < n_row_parts) row_part[b * n_row_parts + slab] = rowterm;
       }
     }
   }
@@ -870,41 +932,39 @@ loss_coeffs_kernel(const float* __restrict__ dist, long long ldd, const long lon
   }
   __syncthreads();
   if (want_r && rh == 0) {
+    float* cp = col_part + static_cast<long long>(blockIdx.x) * K + k0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) if (ok[i]) atomicAdd(col_sum + k0 + i, colsum[i] + csum[cs * 128 + lane * 4 + i]);
+    for (int i = 0; i < 4; ++i) if (ok[i]) cp[i] = colsum[i] + csum[cs * 128 + lane * 4 + i];
   }
-  // deterministic loss: per-block partial, last block reduces all partials in a fixed order in fp64
+  if (warp != 0) return;
+  // deterministic loss: per-block partial, the last block's first warp adds all partials in a fixed order in fp64
   const long long nblocks = static_cast<long long>(gridDim.x) * gridDim.y;
   unsigned int* counter = reinterpret_cast<unsigned int*>(partials);
   partials += 2;
-  if (threadIdx.x == 0) {
+  unsigned int done = 0;
+  if (lane == 0) {
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += lred[i];
     partials[static_cast<long long>(blockIdx.y) * gridDim.x + blockIdx.x] = t;
     __threadfence();
-    const unsigned int done = atomicAdd(counter, 1u);
-    is_last = (done == nblocks - 1);
+    done = atomicAdd(counter, 1u);
   }
-  __syncthreads();
-  if (!is_last) return;
+  done = __shfl_sync(0xffffffffu, done, 0);
+  if (done != nblocks - 1) return;
   __threadfence();
   double acc = 0.0;
-  for (long long i = threadIdx.x; i < nblocks; i += 256) acc += static_cast<double>(__ldcg(partials + i));
-  dred[threadIdx.x] = acc;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) dred[threadIdx.x] += dred[threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    *loss_out = static_cast<float>(dred[0] * static_cast<double>(inv_count));
+  for (long long i = lane; i < nblocks; i += 32) acc += static_cast<double>(__ldcg(partials + i));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    *loss_out = static_cast<float>(acc * static_cast<double>(inv_count));
     *counter = 0u;                                   // restore the zero state for the next call
   }
 }
 
 // Rows per block of the fused loss kernel: as many as keep ~8 blocks per SM in flight (fewer, taller blocks amortise
-// the per-block setup and cut the column-sum atomics), between LC_ROWS and 128.
+// the per-block setup and shorten the column-sum tables), between LC_ROWS and 128.
 inline int loss_rows_per_block(int64_t B, int64_t K, int sms) {
   const int64_t col_blocks = (K + LC_COLS - 1) / LC_COLS;
   int rpb = LC_ROWS;
@@ -912,6 +972,135 @@ inline int loss_rows_per_block(int64_t B, int64_t K, int sms) {
   return rpb;
 }
 
+// ----------------------------------------------------------------------------------------------
+// Fused prototype optimizer step (the reference optimises som_layer.parameters() with torch.optim.AdamW,
+// models/vit_som.py:140-151: default weight decay 0.01, lr and betas from the YAML) + operand staging for the next
+// forward: ONE pass over W, dW, m, v that writes W, m, v and the tf32 hi/lo split (+ row norms / reciprocal norms) of
+// the NEW prototypes, so that the next step's staging kernel handles the latents only.
+// torch.optim.AdamW semantics (non-amsgrad), per element:
+//   w *= 1 - lr * wd;  m = lerp(m, g, 1 - b1);  v = b2 * v + (1 - b2) g^2;
+//   w -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps),  bc1 = 1 - b1^t, bc2 = 1 - b2^t
+// The step count t and the learning rate live in device memory (hp_dev), so a captured CUDA graph replays correctly:
+//   hp_dev[0] = lr, hp_dev[1] = t (the 1-based step count as a float; the caller advances it on the device before the
+//   call), hp_dev[2] = gradient scale (e.g. 1 / world for a summed gradient; 1 otherwise).
+// Block per row (256 threads), rows of up to 8192 elements stay in registers between the update and the staging.
+// ----------------------------------------------------------------------------------------------
+struct AdamHyper { double beta1, beta2, eps, weight_decay; };   // doubles, like torch's Python scalars
+
+__global__ void __launch_bounds__(256)
+adamw_stage_kernel(float* __restrict__ W, long long ldw, const float* __restrict__ dW, long long lddw,
+                   float* __restrict__ m, float* __restrict__ v, long long ldm, long long rows, int dim,
+                   const float* __restrict__ hp_dev, AdamHyper hp, int mode,
+                   float* __restrict__ hi, float* __restrict__ lo, long long ld_out, float* __restrict__ aux) {
+  som::pdl_wait();
+  som::pdl_launch_dependents();
+  const long long row = blockIdx.x;
+  if (row >= rows) return;
+  const float lr = __ldg(hp_dev), t = __ldg(hp_dev + 1), gscale = __ldg(hp_dev + 2);
+  // bias corrections in double like torch's Python scalars (bias_correction2_sqrt = sqrt(1 - beta2^t))
+  const double bc1 = 1.0 - pow(hp.beta1, static_cast<double>(t));
+  const double bc2 = 1.0 - pow(hp.beta2, static_cast<double>(t));
+  const float step_size = static_cast<float>(static_cast<double>(lr) / bc1);
+  const float bc2_sqrt = static_cast<float>(sqrt(bc2));
+  const float decay = static_cast<float>(1.0 - static_cast<double>(lr) * hp.weight_decay);
+  const float omb1 = static_cast<float>(1.0 - hp.beta1), omb2 = static_cast<float>(1.0 - hp.beta2);
+  const float b2 = static_cast<float>(hp.beta2), eps = static_cast<float>(hp.eps);
+  float* wrow = W + row * ldw;
+  const float* grow = dW + row * lddw;
+  float* mrow = m + row * ldm;
+  float* vrow = v + row * ldm;
+  auto update = [&](float w, float g, float& mm, float& vv) {
+    g *= gscale;
+    w *= decay;
+    mm = fmaf(omb1, g - mm, mm);                             // lerp(m, g, 1 - b1)
+    vv = fmaf(omb2, g * g, b2 * vv);
+    const float denom = sqrtf(vv) / bc2_sqrt + eps;
+    return w - step_size * (mm / denom);
+  };
+  const bool vec = (dim & 3) == 0 && (ldw & 3) == 0 && (lddw & 3) == 0 && (ldm & 3) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(dW) | reinterpret_cast<uintptr_t>(m) |
+                     reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  constexpr int CACHE = 8;
+  const bool cached = vec && dim <= CACHE * 256 * 4;
+  float4 cache[CACHE];
+  float ss = 0.f;
+  if (vec) {
+#pragma unroll
+    for (int j = 0; j < CACHE; ++j) cache[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int j = 0;
+    for (int i = threadIdx.x * 4; i < dim; i += 256 * 4, ++j) {
+      float4 w4 = *reinterpret_cast<const float4*>(wrow + i);
+      const float4 g4 = __ldg(reinterpret_cast<const float4*>(grow + i));
+      float4 m4 = *reinterpret_cast<const float4*>(mrow + i);
+      float4 v4 = *reinterpret_cast<const float4*>(vrow + i);
+      w4.x = update(w4.x, g4.x, m4.x, v4.x); w4.y = update(w4.y, g4.y, m4.y, v4.y);
+      w4.z = update(w4.z, g4.z, m4.z, v4.z); w4.w = update(w4.w, g4.w, m4.w, v4.w);
+      *reinterpret_cast<float4*>(wrow + i) = w4;
+      *reinterpret_cast<float4*>(mrow + i) = m4;
+      *reinterpret_cast<float4*>(vrow + i) = v4;
+      ss = fmaf(w4.x, w4.x, ss); ss = fmaf(w4.y, w4.y, ss); ss = fmaf(w4.z, w4.z, ss); ss = fmaf(w4.w, w4.w, ss);
+      if (cached) {
+#pragma unroll
+        for (int jj = 0; jj < CACHE; ++jj) if (jj == j) cache[jj] = w4;     // static register indices
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < dim; i += 256) {
+      float mm = mrow[i], vv = vrow[i];
+      const float w = update(wrow[i], __ldg(grow + i), mm, vv);
+      wrow[i] = w; mrow[i] = mm; vrow[i] = vv;
+      ss = fmaf(w, w, ss);
+    }
+  }
+  if (!hi) return;                                           // optimizer step only (no staging requested)
+  __shared__ float red[8];
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ss += red[i];
+  float denom = 1.f;
+  if (mode == 1) {
+    denom = fmaxf(sqrtf(ss), 1e-12f);                        // F.normalize(p=2, eps=1e-12), as prep_rows_kernel
+    if (threadIdx.x == 0) aux[row] = 1.f / denom;
+  } else if (threadIdx.x == 0) {
+    aux[row] = ss;
+  }
+  float* ph = hi + row * ld_out;
+  float* pl = lo + row * ld_out;
+  const int dim_out = static_cast<int>(ld_out);
+  auto split1 = [&](float x, float& h, float& l) {
+    if (mode == 1) x = x / denom;
+    h = tf32_rna(x);
+    l = tf32_rna(x - h);
+  };
+  if (vec) {
+    int j = 0;
+    for (int i = threadIdx.x * 4; i < dim_out; i += 256 * 4, ++j) {
+      float4 h = make_float4(0.f, 0.f, 0.f, 0.f), l = h;
+      if (i < dim) {
+        float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cached) {
+#pragma unroll
+          for (int jj = 0; jj < CACHE; ++jj) if (jj == j) w4 = cache[jj];
+        } else {
+          w4 = *reinterpret_cast<const float4*>(wrow + i);   // this thread's own store of the update pass
+        }
+        split1(w4.x, h.x, l.x); split1(w4.y, h.y, l.y); split1(w4.z, h.z, l.z); split1(w4.w, h.w, l.w);
+      }
+      *reinterpret_cast<float4*>(ph + i) = h;
+      *reinterpret_cast<float4*>(pl + i) = l;
+    }
+  } else {
+    for (int i = threadIdx.x; i < dim_out; i += 256) {
+      float h = 0.f, l = 0.f;
+      if (i < dim) split1(wrow[i], h, l);
+      ph[i] = h;
+      pl[i] = l;
+    }
+  }
+}
 
 // ----------------------------------------------------------------------------------------------
 // Prototype-gradient all-reduce over NVLink SHARP (NVLS): batch-sharded data parallelism averages dW[K, D] over the
@@ -996,9 +1185,8 @@ int launch_prep(const PrepSet& a, const PrepSet& b, int64_t dim, int mode, int64
   const long long blocks_b = b.src ? (b.rows + per_block - 1) / per_block : 0;
   if (blocks_a + blocks_b > 0x7fffffffLL) return fail(SOM_ERR_ARG, "too many rows to stage in one launch");
   const unsigned grid = static_cast<unsigned>(blocks_a + blocks_b);
-  if (dim <= 1024) prep_rows_kernel<32><<<grid, 256, 0, st>>>(a, b, blocks_a, static_cast<int>(dim), mode, ld_out);
-  else             prep_rows_kernel<256><<<grid, 256, 0, st>>>(a, b, blocks_a, static_cast<int>(dim), mode, ld_out);
-  SOM_CUDA(cudaGetLastError());
+  if (dim <= 1024) SOM_CUDA(launch_kernel(prep_rows_kernel<32>, dim3(grid), dim3(256), 0, st, a, b, blocks_a, static_cast<int>(dim), mode, ld_out));
+  else             SOM_CUDA(launch_kernel(prep_rows_kernel<256>, dim3(grid), dim3(256), 0, st, a, b, blocks_a, static_cast<int>(dim), mode, ld_out));
   g_launches.fetch_add(1);
   return SOM_OK;
 }
@@ -1010,7 +1198,7 @@ int launch_prep(const PrepSet& a, const PrepSet& b, int64_t dim, int mode, int64
 // ------------------------------------------------------------------------------------------------
 extern "C" {
 
-int som_b200_abi_version(void) { return 5; }
+int som_b200_abi_version(void) { return 6; }
 const char* som_last_error(void) { return g_last_error.c_str(); }
 int64_t som_launch_count(void) { return g_launches.load(); }
 void som_launch_count_reset(void) { g_launches.store(0); }
@@ -1020,9 +1208,14 @@ void som_set_tuning(int bn_override, int kchunk) {
 }
 void som_set_debug(int bits) { g_debug.store(bits & ~16); g_tma3d.store((bits & 16) ? 0 : 1); }
 void som_set_debug_times(unsigned long long* dev_buf) { g_dbg_times.store(dev_buf); }
-void som_set_sm_limit(int max_sms) { g_sm_limit.store(max_sms > 0 ? max_sms : 0); }
+void som_set_pdl(int on) { g_pdl.store(on ? 1 : 0); }
 void som_set_streamk(int mode) { g_streamk.store(mode < 0 ? -1 : (mode > 0 ? 1 : 0)); }
-int64_t som_gemm_workspace_floats(void) { return SK_FLAG_WORDS + 74ll * 256 * 256; }
+int64_t som_gemm_workspace_floats(void) {
+  // one 256 x 256 partial tile per CTA pair of the current device (148 SMs -> 74 pairs on a B200)
+  DeviceInfo di;
+  const int64_t pairs = device_info(di) == SOM_OK && di.sms >= 2 ? di.sms / 2 : 74;
+  return SK_FLAG_WORDS + std::min<int64_t>(pairs, SK_FLAG_WORDS / 16) * 256 * 256;
+}
 void som_set_cta_group(int cg) { g_cg_override.store(cg == 1 || cg == 2 ? cg : 0); }
 
 int som_prep_rows(const float* src, int64_t rows, int64_t dim, int64_t ld_src, int mode, float* hi, float* lo,
@@ -1069,9 +1262,9 @@ int som_bmu_decode(const long long* packed, int64_t B, int64_t K_total, int64_t*
   DeviceInfo di;
   if (int rc = device_info(di)) return rc;
   if (!packed || !bmu || B <= 0 || K_total <= 0) return fail(SOM_ERR_ARG, "som_bmu_decode: bad argument");
-  bmu_decode_kernel<<<static_cast<unsigned>((B + 255) / 256), 256, 0, as_stream(stream)>>>(
-      packed, B, K_total, reinterpret_cast<long long*>(bmu), min_key);
-  SOM_CUDA(cudaGetLastError());
+  SOM_CUDA(launch_kernel(bmu_decode_kernel, dim3(static_cast<unsigned>((B + 255) / 256)), dim3(256), 0, as_stream(stream),
+                         packed, static_cast<long long>(B), static_cast<long long>(K_total),
+                         reinterpret_cast<long long*>(bmu), min_key));
   g_launches.fetch_add(1);
   return SOM_OK;
 }
@@ -1188,37 +1381,42 @@ int som_forward(const float* x, int64_t ldx, const float* W, int64_t ldw, int64_
   return SOM_OK;
 }
 
+int som_loss_fused_parts(int64_t B, int64_t K, int64_t* n_row_parts, int64_t* n_col_parts) {
+  DeviceInfo di;
+  if (int rc = device_info(di)) return rc;
+  if (B <= 0 || K <= 0 || !n_row_parts || !n_col_parts) return fail(SOM_ERR_ARG, "som_loss_fused_parts: bad argument");
+  const int rpb = loss_rows_per_block(B, K, di.sms);
+  *n_row_parts = (K + 127) / 128;
+  *n_col_parts = (B + rpb - 1) / rpb;
+  return SOM_OK;
+}
+
 int som_loss_fused(const float* dist, int64_t ldd, const int64_t* bmu, const float* grid_pos, int grid_rows,
                    int grid_cols, int64_t B, int64_t K, int64_t k_offset, const float* T_dev, float inv_count, int mode,
-                   float* r_hi, float* r_lo, int64_t ldr, float* row_sum, float* col_sum, float* scratch,
+                   float* r_hi, float* r_lo, int64_t ldr, float* row_part, float* col_part, float* scratch,
                    float* loss_out, void* stream) {
   DeviceInfo di;
   if (int rc = device_info(di)) return rc;
   if (!dist || !bmu || !grid_pos || !T_dev || !scratch || !loss_out || B <= 0 || K <= 0 || ldd < K)
     return fail(SOM_ERR_ARG, "som_loss_fused: bad argument");
   if (mode != SOM_MODE_EUCLIDEAN && mode != SOM_MODE_COSINE) return fail(SOM_ERR_ARG, "som_loss_fused: bad mode");
-  if (r_hi) {
-    if (!r_lo || !row_sum || !col_sum || ldr < K) return fail(SOM_ERR_ARG, "som_loss_fused: bad backward staging");
-    if (col_sum == row_sum + B) {                       // adjacent (the usual carve-up): one memset node
-      SOM_CUDA(cudaMemsetAsync(row_sum, 0, sizeof(float) * (B + K), as_stream(stream)));
-    } else {
-      SOM_CUDA(cudaMemsetAsync(row_sum, 0, sizeof(float) * B, as_stream(stream)));
-      SOM_CUDA(cudaMemsetAsync(col_sum, 0, sizeof(float) * K, as_stream(stream)));
-    }
-  }
+  if (r_hi && (!r_lo || !row_part || !col_part || ldr < K)) return fail(SOM_ERR_ARG, "som_loss_fused: bad backward staging");
   // grid_rows / grid_cols > 0: the caller vouches that grid_pos is the canonical square grid (cell k at (k / cols, k % cols))
   const bool square = grid_rows > 0 && grid_cols > 0 && grid_rows <= LC_MAX_TAB && grid_cols <= LC_MAX_TAB;
   const int rpb = loss_rows_per_block(B, K, di.sms);
+  const int n_row_parts = static_cast<int>((K + 127) / 128);
   dim3 grid(static_cast<unsigned>((B + rpb - 1) / rpb), static_cast<unsigned>((K + LC_COLS - 1) / LC_COLS));
+  const long long* bmu_ll = reinterpret_cast<const long long*>(bmu);
   if (square)
-    loss_coeffs_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(
-        dist, ldd, reinterpret_cast<const long long*>(bmu), grid_pos, grid_rows, grid_cols, B, K, k_offset, T_dev,
-        inv_count, mode, r_hi, r_lo, ldr, row_sum, col_sum, scratch, loss_out, rpb);
+    SOM_CUDA(launch_kernel(loss_coeffs_kernel<true>, grid, dim3(256), 0, as_stream(stream), dist, static_cast<long long>(ldd),
+                           bmu_ll, grid_pos, grid_rows, grid_cols, static_cast<long long>(B), static_cast<long long>(K),
+                           static_cast<long long>(k_offset), T_dev, inv_count, mode, r_hi, r_lo, static_cast<long long>(ldr),
+                           row_part, n_row_parts, col_part, scratch, loss_out, rpb));
   else
-    loss_coeffs_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(
-        dist, ldd, reinterpret_cast<const long long*>(bmu), grid_pos, 0, 0, B, K, k_offset, T_dev,
-        inv_count, mode, r_hi, r_lo, ldr, row_sum, col_sum, scratch, loss_out, rpb);
-  SOM_CUDA(cudaGetLastError());
+    SOM_CUDA(launch_kernel(loss_coeffs_kernel<false>, grid, dim3(256), 0, as_stream(stream), dist, static_cast<long long>(ldd),
+                           bmu_ll, grid_pos, 0, 0, static_cast<long long>(B), static_cast<long long>(K),
+                           static_cast<long long>(k_offset), T_dev, inv_count, mode, r_hi, r_lo, static_cast<long long>(ldr),
+                           row_part, n_row_parts, col_part, scratch, loss_out, rpb));
   g_launches.fetch_add(1);
   return SOM_OK;
 }
@@ -1228,55 +1426,69 @@ int64_t som_loss_fused_scratch_floats(int64_t B, int64_t K) {
 }
 
 int som_backward_dw(const float* r_hi, const float* r_lo, int64_t ldr, const float* x_hi, const float* x_lo,
-                    int64_t ld_stage, const float* W, int64_t ldw, const float* col_sum, const float* w_aux,
-                    const float* g_dev, int64_t B, int64_t K, int64_t D, int mode, float* dW, int64_t lddw,
-                    int accumulate, float* ws, int64_t ws_floats, void* stream) {
-  if (!W || !col_sum || !g_dev || !dW || ldw < D || lddw < D) return fail(SOM_ERR_ARG, "som_backward_dw: bad argument");
+                    int64_t ld_stage, const float* W, int64_t ldw, const float* col_part, int64_t n_col_parts,
+                    const float* w_aux, const float* g_dev, int64_t B, int64_t K, int64_t D, int mode, float* dW,
+                    int64_t lddw, int accumulate, int sm_limit, float* ws, int64_t ws_floats, void* stream) {
+  if (!W || !col_part || n_col_parts <= 0 || !g_dev || !dW || ldw < D || lddw < D)
+    return fail(SOM_ERR_ARG, "som_backward_dw: bad argument");
   if (mode == SOM_MODE_COSINE && !w_aux) return fail(SOM_ERR_ARG, "som_backward_dw: cosine needs the reciprocal norms");
   som::EpiParams e{};
-  e.sum = col_sum; e.aux = w_aux; e.g_dev = g_dev; e.mode = mode; e.accumulate = accumulate;
+  e.sum = col_part; e.sum_n = static_cast<int>(n_col_parts); e.sum_ld_m = 1; e.sum_ld_j = K;
+  e.aux = w_aux; e.g_dev = g_dev; e.mode = mode; e.accumulate = accumulate;
   e.src = W; e.lds = ldw; e.out = dW; e.ldo = lddw;
   return launch_gemm(som::EPI_GRAD, r_hi, r_lo, ldr, 1, x_hi, x_lo, ld_stage, 1, K, D, B, 0, 0, 3, e, ws, ws_floats,
-                     as_stream(stream));
+                     as_stream(stream), sm_limit);
 }
 
 int som_backward_dx(const float* r_hi, const float* r_lo, int64_t ldr, const float* w_hi, const float* w_lo,
-                    int64_t ld_stage, const float* x, int64_t ldx, const float* row_sum, const float* x_aux,
-                    const float* g_dev, int64_t B, int64_t K, int64_t D, int mode, float* dx, int64_t lddx,
-                    int accumulate, float* ws, int64_t ws_floats, void* stream) {
-  if (!x || !row_sum || !g_dev || !dx || ldx < D || lddx < D) return fail(SOM_ERR_ARG, "som_backward_dx: bad argument");
+                    int64_t ld_stage, const float* x, int64_t ldx, const float* row_part, int64_t n_row_parts,
+                    const float* x_aux, const float* g_dev, int64_t B, int64_t K, int64_t D, int mode, float* dx,
+                    int64_t lddx, int accumulate, int sm_limit, float* ws, int64_t ws_floats, void* stream) {
+  if (!x || !row_part || n_row_parts <= 0 || !g_dev || !dx || ldx < D || lddx < D)
+    return fail(SOM_ERR_ARG, "som_backward_dx: bad argument");
   if (mode == SOM_MODE_COSINE && !x_aux) return fail(SOM_ERR_ARG, "som_backward_dx: cosine needs the reciprocal norms");
   som::EpiParams e{};
-  e.sum = row_sum; e.aux = x_aux; e.g_dev = g_dev; e.mode = mode; e.accumulate = accumulate;
+  e.sum = row_part; e.sum_n = static_cast<int>(n_row_parts); e.sum_ld_m = n_row_parts; e.sum_ld_j = 1;
+  e.aux = x_aux; e.g_dev = g_dev; e.mode = mode; e.accumulate = accumulate;
   e.src = x; e.lds = ldx; e.out = dx; e.ldo = lddx;
   return launch_gemm(som::EPI_GRAD, r_hi, r_lo, ldr, 0, w_hi, w_lo, ld_stage, 1, B, D, K, 0, 0, 3, e, ws, ws_floats,
-                     as_stream(stream));
+                     as_stream(stream), sm_limit);
 }
 
-// Both gradient GEMMs in ONE persistent CTA-pair launch: their tiles form one work list that stream-K spreads evenly
-// over the 74 pairs, so there is one prologue, one tail and no tile-count quantisation per GEMM.  Falls back to the two
-// separate launches when the shapes do not allow a common pair tile (tiny problems) or no workspace was given.
+// Both gradient GEMMs in ONE persistent CTA-pair launch: their tiles form one work list (dW tiles first) that stream-K
+// spreads evenly over the CTA pairs, so there is one prologue, one tail and no tile-count quantisation per GEMM.
+// Falls back to the two separate launches when the shapes do not allow a common pair tile (tiny problems) or no
+// workspace was given.
+// Data parallel: with dw_done != NULL every finished 32-row slab of dW adds 1 to *dw_done (release, gpu scope) and
+// *dw_done_expected receives the final count, so that the exchange of dW can be started from another stream by a
+// stream-ordered wait on that word (som_stream_wait_value) while the dx tiles are still being computed;
+// *dw_done_expected = -1 means "not counted" (fallback launches): order the exchange after the call instead.
 int som_backward_fused(const float* r_hi, const float* r_lo, int64_t ldr, const float* x_hi, const float* x_lo,
                        const float* w_hi, const float* w_lo, int64_t ld_stage, const float* x, int64_t ldx,
-                       const float* W, int64_t ldw, const float* row_sum, const float* col_sum, const float* x_aux,
-                       const float* w_aux, const float* g_dev, int64_t B, int64_t K, int64_t D, int mode, float* dW,
-                       int64_t lddw, int accumulate_dw, float* dx, int64_t lddx, float* ws, int64_t ws_floats,
-                       void* stream) {
-  if (!W || !col_sum || !x || !row_sum || !g_dev || !dW || !dx || ldw < D || lddw < D || ldx < D || lddx < D)
+                       const float* W, int64_t ldw, const float* row_part, int64_t n_row_parts, const float* col_part,
+                       int64_t n_col_parts, const float* x_aux, const float* w_aux, const float* g_dev, int64_t B,
+                       int64_t K, int64_t D, int mode, float* dW, int64_t lddw, int accumulate_dw, float* dx,
+                       int64_t lddx, int sm_limit, unsigned int* dw_done, int64_t* dw_done_expected, float* ws,
+                       int64_t ws_floats, void* stream) {
+  if (dw_done_expected) *dw_done_expected = -1;
+  if (!W || !col_part || !x || !row_part || n_row_parts <= 0 || n_col_parts <= 0 || !g_dev || !dW || !dx || ldw < D ||
+      lddw < D || ldx < D || lddx < D)
     return fail(SOM_ERR_ARG, "som_backward_fused: bad argument");
   if (mode != SOM_MODE_EUCLIDEAN && mode != SOM_MODE_COSINE) return fail(SOM_ERR_ARG, "som_backward_fused: bad mode");
   if (mode == SOM_MODE_COSINE && (!w_aux || !x_aux)) return fail(SOM_ERR_ARG, "som_backward_fused: cosine needs the reciprocal norms");
   int sms = 0;
-  if (int rc = effective_sms(&sms)) return rc;
+  if (int rc = effective_sms(&sms, sm_limit)) return rc;
   if (ws && (reinterpret_cast<uintptr_t>(ws) & 15) != 0) return fail(SOM_ERR_ARG, "workspace must be 16-byte aligned");
   Problem p[2];
   // dW[K,D] = R^T[K,B] . x[B,D]: A = R read MN-major (K contiguous), B = x~ MN-major (D contiguous)
   p[0] = Problem{r_hi, r_lo, ldr, 1, x_hi, x_lo, ld_stage, 1, K, D, B, som::EpiParams{}};
-  p[0].e.sum = col_sum; p[0].e.aux = w_aux; p[0].e.g_dev = g_dev; p[0].e.mode = mode; p[0].e.accumulate = accumulate_dw;
+  p[0].e.sum = col_part; p[0].e.sum_n = static_cast<int>(n_col_parts); p[0].e.sum_ld_m = 1; p[0].e.sum_ld_j = K;
+  p[0].e.aux = w_aux; p[0].e.g_dev = g_dev; p[0].e.mode = mode; p[0].e.accumulate = accumulate_dw;
   p[0].e.src = W; p[0].e.lds = ldw; p[0].e.out = dW; p[0].e.ldo = lddw;
   // dx[B,D] = R[B,K] . W[K,D]: A = R K-major, B = W~ MN-major
   p[1] = Problem{r_hi, r_lo, ldr, 0, w_hi, w_lo, ld_stage, 1, B, D, K, som::EpiParams{}};
-  p[1].e.sum = row_sum; p[1].e.aux = x_aux; p[1].e.g_dev = g_dev; p[1].e.mode = mode; p[1].e.accumulate = 0;
+  p[1].e.sum = row_part; p[1].e.sum_n = static_cast<int>(n_row_parts); p[1].e.sum_ld_m = n_row_parts; p[1].e.sum_ld_j = 1;
+  p[1].e.aux = x_aux; p[1].e.g_dev = g_dev; p[1].e.mode = mode; p[1].e.accumulate = 0;
   p[1].e.src = x; p[1].e.lds = ldx; p[1].e.out = dx; p[1].e.ldo = lddx;
 
   // common tile width: the cheapest stream-K schedule of the joint work list (cost model of pick_tile)
@@ -1300,14 +1512,80 @@ int som_backward_fused(const float* r_hi, const float* r_lo, int64_t ldr, const 
     }
   }
   if (best_bn == 0) {
-    if (int rc = som_backward_dw(r_hi, r_lo, ldr, x_hi, x_lo, ld_stage, W, ldw, col_sum, w_aux, g_dev, B, K, D, mode, dW,
-                                 lddw, accumulate_dw, ws, ws_floats, stream))
+    if (int rc = som_backward_dw(r_hi, r_lo, ldr, x_hi, x_lo, ld_stage, W, ldw, col_part, n_col_parts, w_aux, g_dev, B, K,
+                                 D, mode, dW, lddw, accumulate_dw, sm_limit, ws, ws_floats, stream))
       return rc;
-    return som_backward_dx(r_hi, r_lo, ldr, w_hi, w_lo, ld_stage, x, ldx, row_sum, x_aux, g_dev, B, K, D, mode, dx, lddx,
-                           0, ws, ws_floats, stream);
+    return som_backward_dx(r_hi, r_lo, ldr, w_hi, w_lo, ld_stage, x, ldx, row_part, n_row_parts, x_aux, g_dev, B, K, D,
+                           mode, dx, lddx, 0, sm_limit, ws, ws_floats, stream);
+  }
+  if (dw_done) {
+    p[0].e.done_counter = dw_done;
+    // 16 warp slabs (2 CTAs x 8 epilogue warps) per 256 x bn tile of dW, each counted once by the tile's owner
+    if (dw_done_expected) *dw_done_expected = ((K + 255) / 256) * ((D + best_bn - 1) / best_bn) * 16;
   }
   return launch_pair(som::EPI_GRAD, p, 2, best_bn, static_cast<int>(best_workers), 0, pair_kchunk(g_kchunk.load(), 3),
                      3, ws, sms, as_stream(stream));
+}
+
+// ---- stream-ordered memory operations (driver API cuStreamWaitValue32 / cuStreamWriteValue32) ---------------------
+// The data-parallel exchange of dW is enqueued on a side stream behind "wait until *addr >= value": the wait is
+// executed by the GPU's front end, it occupies no SM while the gradient GEMMs (which raise the word from their
+// epilogue) are still running.  Both operations can be captured in a CUDA graph.
+int som_stream_wait_value(unsigned int* addr, unsigned int value, void* stream) {
+  DeviceInfo di;
+  if (int rc = device_info(di)) return rc;
+  if (!addr || (reinterpret_cast<uintptr_t>(addr) & 3) != 0) return fail(SOM_ERR_ARG, "som_stream_wait_value: bad address");
+  static PFN_cuStreamWaitValue32_v11070 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      return fail(SOM_ERR_CUDA, "cuStreamWaitValue32 entry point not available");
+    fn = reinterpret_cast<PFN_cuStreamWaitValue32_v11070>(p);
+  }
+  const CUresult r = fn(reinterpret_cast<CUstream>(stream), reinterpret_cast<CUdeviceptr>(addr), value, CU_STREAM_WAIT_VALUE_GEQ);
+  if (r != CUDA_SUCCESS) return fail(SOM_ERR_CUDA, "cuStreamWaitValue32 failed with CUresult " + std::to_string(r));
+  return SOM_OK;
+}
+int som_stream_write_value(unsigned int* addr, unsigned int value, void* stream) {
+  DeviceInfo di;
+  if (int rc = device_info(di)) return rc;
+  if (!addr || (reinterpret_cast<uintptr_t>(addr) & 3) != 0) return fail(SOM_ERR_ARG, "som_stream_write_value: bad address");
+  static PFN_cuStreamWriteValue32_v11070 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      return fail(SOM_ERR_CUDA, "cuStreamWriteValue32 entry point not available");
+    fn = reinterpret_cast<PFN_cuStreamWriteValue32_v11070>(p);
+  }
+  const CUresult r = fn(reinterpret_cast<CUstream>(stream), reinterpret_cast<CUdeviceptr>(addr), value, CU_STREAM_WRITE_VALUE_DEFAULT);
+  if (r != CUDA_SUCCESS) return fail(SOM_ERR_CUDA, "cuStreamWriteValue32 failed with CUresult " + std::to_string(r));
+  return SOM_OK;
+}
+
+// ---- prototype optimizer step fused with the operand staging of the next forward ----------------------------------
+int som_adamw_step(float* W, int64_t ldw, const float* dW, int64_t lddw, float* m, float* v, int64_t ldm, int64_t K,
+                   int64_t D, const float* hp_dev, double beta1, double beta2, double eps, double weight_decay, int mode,
+                   float* w_hi, float* w_lo, int64_t ld_stage, float* w_aux, void* stream) {
+  DeviceInfo di;
+  if (int rc = device_info(di)) return rc;
+  if (!W || !dW || !m || !v || !hp_dev || K <= 0 || D <= 0 || D > (1ll << 30) || ldw < D || lddw < D || ldm < D)
+    return fail(SOM_ERR_ARG, "som_adamw_step: bad argument");
+  if (K > 0x7fffffffLL) return fail(SOM_ERR_ARG, "som_adamw_step: too many rows");
+  if (w_hi) {
+    if (!w_lo || !w_aux || ld_stage < D || (ld_stage & 3) != 0 ||
+        ((reinterpret_cast<uintptr_t>(w_hi) | reinterpret_cast<uintptr_t>(w_lo)) & 15) != 0)
+      return fail(SOM_ERR_ARG, "som_adamw_step: bad staging buffers");
+    if (mode != SOM_MODE_EUCLIDEAN && mode != SOM_MODE_COSINE) return fail(SOM_ERR_ARG, "som_adamw_step: bad mode");
+  }
+  AdamHyper hp{beta1, beta2, eps, weight_decay};
+  SOM_CUDA(launch_kernel(adamw_stage_kernel, dim3(static_cast<unsigned>(K)), dim3(256), 0, as_stream(stream), W,
+                         static_cast<long long>(ldw), dW, static_cast<long long>(lddw), m, v, static_cast<long long>(ldm),
+                         static_cast<long long>(K), static_cast<int>(D), hp_dev, hp, mode, w_hi, w_lo,
+                         static_cast<long long>(ld_stage), w_aux));
+  g_launches.fetch_add(1);
+  return SOM_OK;
 }
 
 // In-place mean over the ranks of the fp32 buffer every rank holds at the same offset of a symmetric allocation:

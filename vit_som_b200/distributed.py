@@ -82,10 +82,13 @@ def all_reduce_mean(t: torch.Tensor, group=None) -> torch.Tensor:
 class DataParallelSOM:
     """Attach DDP-equivalent gradient averaging to a :class:`SOMLayer` whose batch is sharded over ranks.
 
-    ``DataParallelSOM(layer)`` broadcasts the prototypes from rank 0 and installs the layer's dW hook: inside the
-    backward, right after the dW GEMM has been enqueued, the all-reduce (+ 1/world scaling) of dW is issued on a
-    communication stream; the dx GEMM then runs concurrently, and the compute stream joins the communication stream
-    before backward returns dW to autograd.  The local loss is the mean over the local rows, as under DDP."""
+    ``DataParallelSOM(layer)`` broadcasts the prototypes from rank 0 and installs itself as the layer's dW hook.  The
+    backward stays ONE launch for both gradient GEMMs (dW tiles first); the exchange of dW (+ 1/world scaling) is
+    enqueued on a communication stream behind a stream-ordered wait on the counter that the dW epilogues raise
+    (``som_stream_wait_value``: executed by the GPU front end, no SM is held while waiting), so it runs under the dx
+    tiles of the same launch - and, in a full model, under the ViT backward.  The GEMM launch leaves a few SMs to the
+    exchange kernel (``gemm_sm_limit``, a per-call argument of the C-ABI).  The compute stream joins the communication
+    stream before backward returns dW to autograd.  The local loss is the mean over the local rows, as under DDP."""
 
     def __init__(self, layer: SOMLayer, group=None, broadcast: bool = True, gemm_sm_limit: int | None = None,
                  nvls: bool | None = None):
@@ -93,18 +96,21 @@ class DataParallelSOM:
             raise SomError("DataParallelSOM needs an initialised torch.distributed process group")
         self.layer, self.group = layer, group
         self.nvls = None
-        # SMs the dx GEMM may occupy while the exchange runs next to it (the other GEMMs of the step use all SMs)
-        self.gemm_sm_limit = int(gemm_sm_limit) if gemm_sm_limit is not None and layer.prototypes.is_cuda else 0
-        self.world = dist.get_world_size(group)
         dev = layer.prototypes.device
-        # lowest priority: when dW's all-reduce and the dx GEMM become runnable together the GEMM's CTA pairs are
-        # placed first and the collective takes the SMs that are left (the GEMM never fills all 148 at these sizes)
+        self.world = dist.get_world_size(group)
+        # SMs the gradient GEMMs may occupy while the exchange runs beside them (0 = all)
+        self.gemm_sm_limit = int(gemm_sm_limit) if gemm_sm_limit is not None and dev.type == "cuda" else 0
+        # lowest priority: when the exchange and GEMM tiles become runnable together the GEMM's CTA pairs are placed first
         self.comm_stream = torch.cuda.Stream(dev, priority=0) if dev.type == "cuda" else None
+        self._counter = torch.zeros(4, device=dev, dtype=torch.int32) if dev.type == "cuda" else None
         if broadcast:
+            # in place on the parameter itself (not on .data): the version counter moves, so a prototype staging that
+            # was cached before wrapping is not reused with the broadcast values
             with torch.no_grad():
-                dist.broadcast(layer.prototypes.data, src=dist.get_global_rank(group, 0) if group is not None else 0,
+                dist.broadcast(layer.prototypes, src=dist.get_global_rank(group, 0) if group is not None else 0,
                                group=group)
-        layer._dw_hook = self._on_dw
+        layer.invalidate_staging()
+        layer._dw_hook = self
         want_nvls = nvls if nvls is not None else os.environ.get("SOM_DP_NVLS", "1") != "0"
         if want_nvls and dev.type == "cuda" and self.world > 1:
             self.nvls = self._setup_nvls(layer, dev)
@@ -144,32 +150,62 @@ class DataParallelSOM:
         layer._dw_out = state["dw"]
         return state
 
-    def _on_dw(self, dw: torch.Tensor):
-        """Called from FusedLossFn.backward with the freshly enqueued dW; returns the join callable."""
+    # ---- hook protocol (called from ops.FusedLossFn.backward) ----------------------------------------------------
+    def counter_ptr(self):
+        """Device word the dW epilogues raise; also forks the communication stream off the compute stream (what is
+        enqueued on it afterwards is ordered behind everything that precedes the backward launch - and belongs to the
+        same CUDA-graph capture)."""
+        if self.comm_stream is None:
+            return None
+        self.comm_stream.wait_stream(torch.cuda.current_stream(self._counter.device))
+        return self._counter.data_ptr()
+
+    def _reduce(self, dw: torch.Tensor):
+        nv = self.nvls
+        if nv is not None and dw.data_ptr() == nv["dw"].data_ptr():
+            from . import _lib
+            _lib.check(_lib.lib().som_allreduce_mean_nvls(nv["mc"], nv["flag_ptrs"], nv["n"], dist.get_rank(self.group),
+                                                          self.world, _lib.stream_ptr(dw.device)), "som_allreduce_mean_nvls")
+        else:
+            all_reduce_mean(dw, self.group)
+
+    def exchange_counted(self, dw: torch.Tensor, expected: int):
+        """The fused backward launch is enqueued and will raise the counter to ``expected`` when its last dW tile is
+        written: wait for that on the communication stream, reset the word, run the exchange.  Returns the join."""
+        from . import _lib
+        L = _lib.lib()
+        cur = torch.cuda.current_stream(dw.device)
+        with torch.cuda.stream(self.comm_stream):
+            sp = _lib.stream_ptr(dw.device)
+            _lib.check(L.som_stream_wait_value(self._counter.data_ptr(), expected, sp), "som_stream_wait_value")
+            _lib.check(L.som_stream_write_value(self._counter.data_ptr(), 0, sp), "som_stream_write_value")
+            self._reduce(dw)
+        dw.record_stream(self.comm_stream)
+        return lambda: cur.wait_stream(self.comm_stream)
+
+    def exchange_after(self, dw: torch.Tensor):
+        """dW has been enqueued by a kernel of its own on the current stream: exchange it once that kernel is done
+        (beside whatever the compute stream runs next).  Returns the join callable (None on CPU tensors)."""
         if self.comm_stream is None:                       # CPU tensors (gloo unit tests)
             all_reduce_mean(dw, self.group)
             return None
         cur = torch.cuda.current_stream(dw.device)
         self.comm_stream.wait_stream(cur)
         with torch.cuda.stream(self.comm_stream):
-            nv = self.nvls
-            if nv is not None and dw.data_ptr() == nv["dw"].data_ptr():
-                from . import _lib
-                _lib.check(_lib.lib().som_allreduce_mean_nvls(nv["mc"], nv["flag_ptrs"], nv["n"], dist.get_rank(self.group),
-                                                              self.world, _lib.stream_ptr()), "som_allreduce_mean_nvls")
-            else:
-                all_reduce_mean(dw, self.group)
+            self._reduce(dw)
         dw.record_stream(self.comm_stream)
-        if self.gemm_sm_limit:
-            from . import _lib
-            L = _lib.lib()
-            L.som_set_sm_limit(self.gemm_sm_limit)         # host-side launch parameter of the dx GEMM that follows
-
-            def join():
-                L.som_set_sm_limit(0)
-                cur.wait_stream(self.comm_stream)
-            return join
         return lambda: cur.wait_stream(self.comm_stream)
+
+    _on_dw = exchange_after
+
+    def reduce_accumulator(self):
+        """Row-chunked batches accumulate dW in ``layer.grad_accumulator`` with the hook detached (see ``detach``);
+        call this once after the last chunk to average the accumulated gradient over the ranks."""
+        acc = self.layer.grad_accumulator
+        if acc is None:
+            raise SomError("no grad_accumulator is set on the layer")
+        all_reduce_mean(acc, self.group)
+        return acc
 
     def detach(self):
         self.layer._dw_hook = None
@@ -202,7 +238,7 @@ class _ShardedLossFn(torch.autograd.Function):
                 # symmetric buffer; autograd gets a private copy because the buffer is reused by the next call
                 from . import _lib
                 _lib.check(_lib.lib().som_allreduce_nvls(nv["mc"], nv["flag_ptrs"], nv["n"], nv["rank"], nv["world"],
-                                                         1.0, _lib.stream_ptr()), "som_allreduce_nvls")
+                                                         1.0, _lib.stream_ptr(dx.device)), "som_allreduce_nvls")
                 grads = (dx.clone(),) + tuple(grads[1:])
             else:
                 all_reduce_sum(dx, ctx.group)
@@ -231,6 +267,37 @@ class PrototypeShardedSOM(SOMLayer):
         self.prototypes = torch.nn.Parameter(full[self.k_begin:self.k_end].clone())
         self._nvls_dx = {}                    # (B, D) -> symmetric dx buffer + multicast mapping (None: NCCL)
         self.use_nvls = os.environ.get("SOM_DP_NVLS", "1") != "0"
+
+    # ---- checkpoints: the state dict holds the FULL map under the reference's key ---------------------------------
+    def gather_prototypes(self) -> torch.Tensor:
+        """The full [K, D] map assembled from the shards of all ranks (a collective: every rank must call it)."""
+        local = self.prototypes.detach()
+        sizes = [shard_range(self.k_total, self.world, r) for r in range(self.world)]
+        longest = max(e - b for b, e in sizes)
+        padded = local.new_zeros((longest, local.shape[1]))
+        padded[:local.shape[0]] = local
+        parts = [torch.empty_like(padded) for _ in range(self.world)]
+        dist.all_gather(parts, padded, group=self.group)
+        return torch.cat([p[:e - b] for p, (b, e) in zip(parts, sizes)], dim=0)
+
+    def state_dict(self, *args, **kwargs):
+        """Same keys and shapes as the unsharded layer (``prototypes`` [K, D], ``grid_positions``): a checkpoint written
+        by a sharded run loads into ``SOMLayer`` / the reference and vice versa.  Collective (all ranks call it)."""
+        sd = super().state_dict(*args, **kwargs)
+        prefix = kwargs.get("prefix", args[1] if len(args) > 1 else "")
+        key = prefix + "prototypes"
+        if key in sd:
+            sd[key] = self.gather_prototypes()
+        return sd
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        key = prefix + "prototypes"
+        full = state_dict.get(key)
+        if full is not None and full.shape[0] == self.k_total and self.k_total != self.prototypes.shape[0]:
+            state_dict = dict(state_dict)
+            state_dict[key] = full[self.k_begin:self.k_end]       # this rank's block of the full map
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+        self.invalidate_staging()
 
     def _nvls_dx_buffer(self, B: int, D: int, dev):
         """Symmetric [B, D] buffer for the partial dx of this rank plus what som_allreduce_nvls needs; allocated and
@@ -281,7 +348,7 @@ class PrototypeShardedSOM(SOMLayer):
             state, _ = ops.forward(x, self.prototypes, mode, ws, refill, want_dist=want_dist, want_bmu=False,
                                    idx_offset=self.k_begin, k_total=self.k_total)
         except Exception:
-            self._w_cache = None
+            self.invalidate_staging()
             raise
         reduce_packed_min(state.packed, self.group)          # exchange step 1: B x 8 bytes over NVLink
         bmu = ops.bmu_decode(state.packed, self.k_total)

@@ -17,7 +17,13 @@ class StepGraph:
     ``step_fn()`` must read its inputs from tensors that stay allocated (copy new data INTO them before a replay)
     and return a tensor (or tuple of tensors); the returned objects are the static outputs of every replay.
     Gradients written by the step (``x.grad``, ``prototypes.grad``) live in graph-owned memory as well: read them
-    after ``replay()`` on the same stream."""
+    after ``replay()`` on the same stream.
+
+    Prototype updates between replays are honoured: under capture ``SOMLayer`` always puts the staging of the prototypes
+    INTO the captured step (it re-reads the parameter on every replay), or reads the buffer that
+    ``FusedPrototypeAdamW`` rewrites in place - a replay never computes with the prototypes of capture time.  (An
+    optimizer that REPLACES ``layer.prototypes`` by a new tensor, instead of updating it in place, needs a re-capture,
+    as with any CUDA graph.)"""
 
     def __init__(self, step_fn, warmup: int = 2, stream: torch.cuda.Stream | None = None):
         self.stream = stream if stream is not None else torch.cuda.current_stream()

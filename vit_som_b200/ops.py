@@ -8,11 +8,16 @@ Launches per training step (reference call sequence models/vit_som.py:82-86 + ba
 
     forward   som_forward      staging kernel (x and, when stale, W) -> tcgen05 GEMM + distance/argmin epilogue
                                -> BMU decode                                                       3 launches
-    loss      som_loss_fused   loss + backward staging (R hi/lo, row/column sums) in one pass       1 launch
-    backward  som_backward_dw  tcgen05 GEMM  R^T x~  with the gradient epilogue                     1 launch
-              som_backward_dx  tcgen05 GEMM  R W~    with the gradient epilogue                     1 launch
+    loss      som_loss_fused     loss + backward staging (R hi/lo, partial row/column sums), one pass  1 launch
+    backward  som_backward_fused both gradient GEMMs (R^T x~ and R W~, gradient epilogue)              1 launch
+
+Every wrapper runs on the device of its tensors (device guard + that device's current stream), whatever the
+process-wide current device is.
 """
 from __future__ import annotations
+
+import contextlib
+import ctypes
 
 import torch
 
@@ -43,6 +48,21 @@ def _pad4(n: int) -> int:
     return (n + 3) // 4 * 4
 
 
+def _guard(device):
+    """Make ``device`` current for the enclosed C-ABI calls (the library launches on the current device)."""
+    if device.index is None or torch.cuda.current_device() == device.index:
+        return contextlib.nullcontext()
+    return torch.cuda.device(device)
+
+
+def _grid_f32(grid_pos: torch.Tensor, device) -> torch.Tensor:
+    """grid_positions as the contiguous fp32 tensor on ``device`` the kernels read through a raw pointer
+    (module.half() / .double() casts the registered buffer)."""
+    if grid_pos.dtype != torch.float32 or grid_pos.device != device or not grid_pos.is_contiguous():
+        grid_pos = grid_pos.to(device=device, dtype=torch.float32).contiguous()
+    return grid_pos
+
+
 def _require_cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
     if not isinstance(t, torch.Tensor):
         raise TypeError(f"{name} must be a torch.Tensor")
@@ -63,7 +83,7 @@ def _rowmajor(t: torch.Tensor) -> torch.Tensor:
 class Staging:
     """tf32 hi/lo split of a row-major [rows, dim] matrix plus its per-row aux vector (|row|^2 for euclidean,
     1/max(|row|, eps) for cosine), carved out of one flat allocation: hi | lo | aux."""
-    __slots__ = ("buf", "rows", "dim", "ld", "mode", "hi", "lo", "aux", "key")
+    __slots__ = ("buf", "rows", "dim", "ld", "mode", "hi", "lo", "aux", "key", "from_optimizer")
 
     def __init__(self, rows: int, dim: int, mode: int, device):
         if rows <= 0 or dim <= 0:
@@ -75,6 +95,7 @@ class Staging:
         base = self.buf.data_ptr()
         self.hi, self.lo, self.aux = base, base + 4 * n, base + 8 * n
         self.key = None                       # identity of the tensor version staged here (prototype cache)
+        self.from_optimizer = False           # filled by the fused optimizer kernel for the parameter version in `key`
 
     def aux_tensor(self) -> torch.Tensor:
         n = self.rows * self.ld
@@ -87,8 +108,9 @@ def stage_rows(src: torch.Tensor, mode: int) -> Staging:
     if src.dim() != 2:
         raise ValueError("operand must be 2-D")
     st = Staging(src.shape[0], src.shape[1], mode, src.device)
-    check(_lib.lib().som_prep_rows(ptr(src), st.rows, st.dim, src.stride(0), mode, st.hi, st.lo, st.ld, st.aux,
-                                   stream_ptr()), "som_prep_rows")
+    with _guard(src.device):
+        check(_lib.lib().som_prep_rows(ptr(src), st.rows, st.dim, src.stride(0), mode, st.hi, st.lo, st.ld, st.aux,
+                                       stream_ptr(src.device)), "som_prep_rows")
     return st
 
 
@@ -108,42 +130,45 @@ def forward(x: torch.Tensor, W: torch.Tensor, mode: int, ws: Staging | None = No
     Wf = _rowmajor(_require_cuda_f32(W, "prototypes"))
     if xf.dim() != 2 or Wf.dim() != 2 or xf.shape[1] != Wf.shape[1]:
         raise ValueError("latents [B, D] and prototypes [K, D] do not match")
+    if xf.device != Wf.device:
+        raise SomError(f"latents on {xf.device} but prototypes on {Wf.device}")
     B, D = xf.shape
     K = Wf.shape[0]
     if B == 0:
         raise ValueError("empty batch")
     dev = xf.device
-    xs = Staging(B, D, mode, dev)
-    if ws is None:
-        ws, stage_w = Staging(K, D, mode, dev), True
-    elif ws.rows != K or ws.dim != D or ws.mode != mode:
-        raise ValueError("prototype staging does not match the prototypes")
-    ldd = _pad4(K)
-    dist_buf = torch.empty((B, ldd), device=dev, dtype=torch.float32) if want_dist else None
-    packed = torch.empty((B,), device=dev, dtype=torch.int64)
-    bmu = torch.empty((B,), device=dev, dtype=torch.int64) if want_bmu else None
-    L = _lib.lib()
-    gws, gws_n = gemm_workspace(dev)
-    if GEMM_TIMERS is None:
-        check(L.som_forward(
-            ptr(xf), xf.stride(0), ptr(Wf), Wf.stride(0), B, K, D, mode, 1 if stage_w else 0, idx_offset,
-            xs.hi, xs.lo, xs.aux, ws.hi, ws.lo, ws.aux, xs.ld, ptr(dist_buf), ldd, ptr(packed), ptr(bmu),
-            k_total if k_total is not None else K, gws, gws_n, stream_ptr()), "som_forward")
-    else:
-        # instrumented run (bench.py roofline leg): the same launches issued one by one so that the CUDA events
-        # bracket the tensor-core kernel alone
-        check(L.som_prep_rows(ptr(xf), B, D, xf.stride(0), mode, xs.hi, xs.lo, xs.ld, xs.aux, stream_ptr()),
-              "som_prep_rows")
-        if stage_w:
-            check(L.som_prep_rows(ptr(Wf), K, D, Wf.stride(0), mode, ws.hi, ws.lo, ws.ld, ws.aux, stream_ptr()),
-                  "som_prep_rows")
-        check(L.som_bmu_init(ptr(packed), B, stream_ptr()), "som_bmu_init")
-        check(_gemm("fwd", lambda: L.som_fwd_distances(xs.hi, xs.lo, xs.ld, xs.aux, ws.hi, ws.lo, ws.ld, ws.aux,
-                                                       B, K, D, mode, idx_offset, ptr(dist_buf), ldd, ptr(packed),
-                                                       gws, gws_n, stream_ptr())), "som_fwd_distances")
-        if bmu is not None:
-            check(L.som_bmu_decode(ptr(packed), B, k_total if k_total is not None else K, ptr(bmu), None,
-                                   stream_ptr()), "som_bmu_decode")
+    with _guard(dev):
+        sp = stream_ptr(dev)
+        xs = Staging(B, D, mode, dev)
+        if ws is None:
+            ws, stage_w = Staging(K, D, mode, dev), True
+        elif ws.rows != K or ws.dim != D or ws.mode != mode:
+            raise ValueError("prototype staging does not match the prototypes")
+        ldd = _pad4(K)
+        dist_buf = torch.empty((B, ldd), device=dev, dtype=torch.float32) if want_dist else None
+        packed = torch.empty((B,), device=dev, dtype=torch.int64)
+        bmu = torch.empty((B,), device=dev, dtype=torch.int64) if want_bmu else None
+        L = _lib.lib()
+        gws, gws_n = gemm_workspace(dev)
+        if GEMM_TIMERS is None:
+            check(L.som_forward(
+                ptr(xf), xf.stride(0), ptr(Wf), Wf.stride(0), B, K, D, mode, 1 if stage_w else 0, idx_offset,
+                xs.hi, xs.lo, xs.aux, ws.hi, ws.lo, ws.aux, xs.ld, ptr(dist_buf), ldd, ptr(packed), ptr(bmu),
+                k_total if k_total is not None else K, gws, gws_n, sp), "som_forward")
+        else:
+            # instrumented run (bench.py roofline leg): the same launches issued one by one so that the CUDA events
+            # bracket the tensor-core kernel alone
+            check(L.som_prep_rows(ptr(xf), B, D, xf.stride(0), mode, xs.hi, xs.lo, xs.ld, xs.aux, sp), "som_prep_rows")
+            if stage_w:
+                check(L.som_prep_rows(ptr(Wf), K, D, Wf.stride(0), mode, ws.hi, ws.lo, ws.ld, ws.aux, sp),
+                      "som_prep_rows")
+            check(L.som_bmu_init(ptr(packed), B, sp), "som_bmu_init")
+            check(_gemm("fwd", lambda: L.som_fwd_distances(xs.hi, xs.lo, xs.ld, xs.aux, ws.hi, ws.lo, ws.ld, ws.aux,
+                                                           B, K, D, mode, idx_offset, ptr(dist_buf), ldd, ptr(packed),
+                                                           gws, gws_n, sp)), "som_fwd_distances")
+            if bmu is not None:
+                check(L.som_bmu_decode(ptr(packed), B, k_total if k_total is not None else K, ptr(bmu), None, sp),
+                      "som_bmu_decode")
     st = ForwardState()
     st.x, st.W, st.xs, st.ws, st.mode = xf, Wf, xs, ws, mode
     st.B, st.K, st.D, st.dist_buf, st.ldd, st.packed, st.idx_offset = B, K, D, dist_buf, ldd, packed, idx_offset
@@ -156,18 +181,23 @@ def forward(x: torch.Tensor, W: torch.Tensor, mode: int, ws: Staging | None = No
 
 def bmu_decode(packed: torch.Tensor, k_total: int, want_min: bool = False):
     B = packed.shape[0]
-    bmu = torch.empty((B,), device=packed.device, dtype=torch.int64)
-    mn = torch.empty((B,), device=packed.device, dtype=torch.float32) if want_min else None
-    check(_lib.lib().som_bmu_decode(ptr(packed), B, k_total, ptr(bmu), ptr(mn), stream_ptr()), "som_bmu_decode")
+    dev = packed.device
+    bmu = torch.empty((B,), device=dev, dtype=torch.int64)
+    mn = torch.empty((B,), device=dev, dtype=torch.float32) if want_min else None
+    with _guard(dev):
+        check(_lib.lib().som_bmu_decode(ptr(packed), B, k_total, ptr(bmu), ptr(mn), stream_ptr(dev)), "som_bmu_decode")
     return (bmu, mn) if want_min else bmu
 
 
 def neighbourhood(bmu: torch.Tensor, grid_pos: torch.Tensor, T_dev: torch.Tensor, K: int, k_offset: int = 0):
     B = bmu.shape[0]
+    dev = bmu.device
     ldw = _pad4(K)
-    w = torch.empty((B, ldw), device=bmu.device, dtype=torch.float32)
-    check(_lib.lib().som_neighbourhood(ptr(bmu), ptr(grid_pos), B, K, k_offset, ptr(T_dev), ptr(w), ldw, stream_ptr()),
-          "som_neighbourhood")
+    grid_pos = _grid_f32(grid_pos, dev)
+    w = torch.empty((B, ldw), device=dev, dtype=torch.float32)
+    with _guard(dev):
+        check(_lib.lib().som_neighbourhood(ptr(bmu), ptr(grid_pos), B, K, k_offset, ptr(T_dev), ptr(w), ldw,
+                                           stream_ptr(dev)), "som_neighbourhood")
     return w[:, :K]
 
 
@@ -181,7 +211,9 @@ def gemm_workspace(device):
     buf = _gemm_ws.get(key)
     if buf is None:
         # zero-filled once: the head of the workspace holds the stream-K hand-over flags (the kernels restore zeros)
-        buf = torch.zeros((int(_lib.lib().som_gemm_workspace_floats()),), device=device, dtype=torch.float32)
+        with _guard(device):
+            n = int(_lib.lib().som_gemm_workspace_floats())
+        buf = torch.zeros((n,), device=device, dtype=torch.float32)
         _gemm_ws[key] = buf
     return buf.data_ptr(), buf.numel()
 
@@ -195,6 +227,14 @@ def _loss_scratch(device, n: int) -> torch.Tensor:
     return buf
 
 
+def loss_parts(B: int, K: int, device) -> tuple[int, int]:
+    """(n_row_parts, n_col_parts): sizes of the partial-sum tables ``som_loss_fused`` writes for this shape."""
+    nr, nc = ctypes.c_int64(0), ctypes.c_int64(0)
+    with _guard(device):
+        check(_lib.lib().som_loss_fused_parts(B, K, ctypes.addressof(nr), ctypes.addressof(nc)), "som_loss_fused_parts")
+    return int(nr.value), int(nc.value)
+
+
 def _grad_scalar(g_out: torch.Tensor) -> torch.Tensor:
     g = g_out.reshape(1)
     if g.dtype != torch.float32:
@@ -206,31 +246,44 @@ class FusedLossFn(torch.autograd.Function):
     """loss = inv_count * sum_k w(bmu, T)[b,k] * dist(x, W)[b,k] as ONE autograd node over (x, W).
 
     Forward is one kernel over the distances the layer's forward already produced (``state``): it emits the loss
-    and, when a gradient will be needed, the staged backward operand R and its row/column sums.  Backward is the
-    two tcgen05 gradient GEMMs; the upstream gradient enters through their epilogue.  The B x K weight matrix and
-    the B x K upstream-gradient matrix of the reference's autograd graph are never formed.
-    (models/som_layer.py:137-152 + MeanBackward0 -> MulBackward0 -> EuclideanDistBackward0 | MmBackward0)"""
+    and, when a gradient will be needed, the staged backward operand R and its partial row/column sums.  Backward is
+    the two tcgen05 gradient GEMMs in one launch; the upstream gradient enters through their epilogue.  The B x K
+    weight matrix and the B x K upstream-gradient matrix of the reference's autograd graph are never formed.
+    (models/som_layer.py:137-152 + MeanBackward0 -> MulBackward0 -> EuclideanDistBackward0 | MmBackward0)
+
+    ``dw_hook`` (data parallel, see distributed.DataParallelSOM): an object with ``gemm_sm_limit``, ``counter_ptr()``,
+    ``exchange_counted(dw, expected)`` and ``exchange_after(dw)``; the last two return a join callable."""
 
     @staticmethod
     def forward(ctx, x, W, state, bmu, grid_pos, T_dev, inv_count, k_offset, want_grad, dw_hook, grid_dims=(0, 0)):
         B, K = state.B, state.K
         dev = state.dist_buf.device
         L = _lib.lib()
+        grid_pos = _grid_f32(grid_pos, dev)
+        if T_dev.device != dev or T_dev.dtype != torch.float32:
+            T_dev = T_dev.to(device=dev, dtype=torch.float32)
+        if dw_hook is not None and state.grad_accum is not None:
+            raise SomError("grad_accumulator and a data-parallel wrapper are both set: the in-place accumulated "
+                           "prototype gradient would never be exchanged (use DataParallelSOM.reduce_accumulator() "
+                           "after the last chunk and detach the hook, or drop the accumulator)")
         loss = torch.empty((), device=dev, dtype=torch.float32)
-        scratch = _loss_scratch(dev, int(L.som_loss_fused_scratch_floats(B, K)))
         ldr = _pad4(K)
-        if want_grad:
-            rbuf = torch.empty((2 * B * ldr + B + K,), device=dev, dtype=torch.float32)
-            base = rbuf.data_ptr()
-            r_hi, r_lo = base, base + 4 * B * ldr
-            row_sum, col_sum = base + 8 * B * ldr, base + 8 * B * ldr + 4 * B
-        else:
-            rbuf, r_hi, r_lo, row_sum, col_sum = None, None, None, None, None
-        check(L.som_loss_fused(ptr(state.dist_buf), state.ldd, ptr(bmu), ptr(grid_pos), int(grid_dims[0]),
-                               int(grid_dims[1]), B, K, k_offset, ptr(T_dev),
-                               inv_count, state.mode, r_hi, r_lo, ldr, row_sum, col_sum, ptr(scratch), ptr(loss),
-                               stream_ptr()), "som_loss_fused")
-        ctx.state, ctx.rbuf, ctx.ptrs, ctx.ldr = state, rbuf, (r_hi, r_lo, row_sum, col_sum), ldr
+        with _guard(dev):
+            scratch = _loss_scratch(dev, int(L.som_loss_fused_scratch_floats(B, K)))
+            if want_grad:
+                nrp, ncp = loss_parts(B, K, dev)
+                rbuf = torch.empty((2 * B * ldr + B * nrp + ncp * K,), device=dev, dtype=torch.float32)
+                base = rbuf.data_ptr()
+                r_hi, r_lo = base, base + 4 * B * ldr
+                row_part = base + 8 * B * ldr
+                col_part = row_part + 4 * B * nrp
+            else:
+                rbuf, r_hi, r_lo, row_part, col_part, nrp, ncp = None, None, None, None, None, 0, 0
+            check(L.som_loss_fused(ptr(state.dist_buf), state.ldd, ptr(bmu), ptr(grid_pos), int(grid_dims[0]),
+                                   int(grid_dims[1]), B, K, k_offset, ptr(T_dev),
+                                   inv_count, state.mode, r_hi, r_lo, ldr, row_part, col_part, ptr(scratch), ptr(loss),
+                                   stream_ptr(dev)), "som_loss_fused")
+        ctx.state, ctx.rbuf, ctx.ptrs, ctx.ldr = state, rbuf, (r_hi, r_lo, row_part, nrp, col_part, ncp), ldr
         ctx.x_dtype, ctx.x_shape, ctx.dw_hook = x.dtype, x.shape, dw_hook
         ctx.save_for_backward(bmu, grid_pos, T_dev)     # keeps them alive; the kernels no longer need them
         return loss
@@ -240,50 +293,65 @@ class FusedLossFn(torch.autograd.Function):
         st = ctx.state
         if ctx.rbuf is None:
             raise SomError("som_loss was evaluated without gradient staging (no_grad) but backward was requested")
-        r_hi, r_lo, row_sum, col_sum = ctx.ptrs
+        r_hi, r_lo, row_part, nrp, col_part, ncp = ctx.ptrs
         B, K, D, mode = st.B, st.K, st.D, st.mode
         dev = st.dist_buf.device
         L = _lib.lib()
         g = _grad_scalar(g_out)
-        gws, gws_n = gemm_workspace(dev)
+        if g.device != dev:
+            g = g.to(dev)
+        hook = ctx.dw_hook
+        sm_limit = int(getattr(hook, "gemm_sm_limit", 0) or 0) if hook is not None else 0
         dx = dw = join = None
         acc_buf = st.grad_accum                 # row-chunked batches: the GEMM epilogue adds into this [K, D] buffer
-        if ctx.needs_input_grad[0] and ctx.needs_input_grad[1] and ctx.dw_hook is None and FUSE_BACKWARD:
-            # both gradients, nobody waiting for dW alone: ONE persistent launch over the tiles of both GEMMs
-            dw = acc_buf if acc_buf is not None else torch.empty((K, D), device=dev, dtype=torch.float32)
-            dx = st.dx_out if st.dx_out is not None else torch.empty((B, D), device=dev, dtype=torch.float32)
-            check(_gemm("dw+dx", lambda: L.som_backward_fused(
-                r_hi, r_lo, ctx.ldr, st.xs.hi, st.xs.lo, st.ws.hi, st.ws.lo, st.xs.ld, ptr(st.x), st.x.stride(0),
-                ptr(st.W), st.W.stride(0), row_sum, col_sum, st.xs.aux, st.ws.aux, ptr(g), B, K, D, mode,
-                ptr(dw), dw.stride(0), 1 if acc_buf is not None else 0, ptr(dx), D, gws, gws_n, stream_ptr())),
-                "som_backward_fused")
-            if acc_buf is not None:
-                dw = None                       # already accumulated in place: nothing for autograd to add
-            if dx.dtype != ctx.x_dtype:
-                dx = dx.to(ctx.x_dtype)
-            return dx.view(ctx.x_shape), dw, None, None, None, None, None, None, None, None, None
-        if ctx.needs_input_grad[1]:
-            dw = acc_buf if acc_buf is not None else (
-                st.dw_out if st.dw_out is not None else torch.empty((K, D), device=dev, dtype=torch.float32))
-            check(_gemm("dw", lambda: L.som_backward_dw(r_hi, r_lo, ctx.ldr, st.xs.hi, st.xs.lo, st.xs.ld, ptr(st.W),
-                                                        st.W.stride(0), col_sum, st.ws.aux, ptr(g), B, K, D, mode,
-                                                        ptr(dw), dw.stride(0), 1 if acc_buf is not None else 0,
-                                                        gws, gws_n, stream_ptr())), "som_backward_dw")
-            if acc_buf is not None:
-                dw = None                       # already accumulated in place: nothing for autograd to add
-            elif ctx.dw_hook is not None:
-                join = ctx.dw_hook(dw)          # data-parallel: start the prototype-gradient all-reduce now
-        if ctx.needs_input_grad[0]:
-            dx = st.dx_out if st.dx_out is not None else torch.empty((B, D), device=dev, dtype=torch.float32)
-            check(_gemm("dx", lambda: L.som_backward_dx(r_hi, r_lo, ctx.ldr, st.ws.hi, st.ws.lo, st.ws.ld, ptr(st.x),
-                                                        st.x.stride(0), row_sum, st.xs.aux, ptr(g), B, K, D, mode,
-                                                        ptr(dx), D, 0, gws, gws_n, stream_ptr())), "som_backward_dx")
-            if dx.dtype != ctx.x_dtype:
-                dx = dx.to(ctx.x_dtype)
-            dx = dx.view(ctx.x_shape)
-        if join is not None:
-            join()                              # compute stream waits for the communication stream
-        return dx, dw, None, None, None, None, None, None, None, None, None
+        nothing = (None,) * 9
+        with _guard(dev):
+            sp = stream_ptr(dev)
+            gws, gws_n = gemm_workspace(dev)
+            if ctx.needs_input_grad[0] and ctx.needs_input_grad[1] and FUSE_BACKWARD:
+                # both gradients: ONE persistent launch over the tiles of both GEMMs (dW tiles first)
+                dw = acc_buf if acc_buf is not None else (
+                    st.dw_out if st.dw_out is not None else torch.empty((K, D), device=dev, dtype=torch.float32))
+                dx = st.dx_out if st.dx_out is not None else torch.empty((B, D), device=dev, dtype=torch.float32)
+                counter = hook.counter_ptr() if hook is not None else None
+                expected = ctypes.c_int64(-1)
+                check(_gemm("dw+dx", lambda: L.som_backward_fused(
+                    r_hi, r_lo, ctx.ldr, st.xs.hi, st.xs.lo, st.ws.hi, st.ws.lo, st.xs.ld, ptr(st.x), st.x.stride(0),
+                    ptr(st.W), st.W.stride(0), row_part, nrp, col_part, ncp, st.xs.aux, st.ws.aux, ptr(g), B, K, D, mode,
+                    ptr(dw), dw.stride(0), 1 if acc_buf is not None else 0, ptr(dx), dx.stride(0), sm_limit, counter,
+                    ctypes.addressof(expected), gws, gws_n, sp)), "som_backward_fused")
+                if hook is not None:
+                    # data parallel: the exchange of dW starts as soon as its last tile is written (a stream-ordered
+                    # wait on the counter the dW epilogues raise), under the dx tiles of the same launch
+                    join = (hook.exchange_counted(dw, int(expected.value)) if expected.value >= 0
+                            else hook.exchange_after(dw))
+                if acc_buf is not None:
+                    dw = None                   # already accumulated in place: nothing for autograd to add
+            else:
+                if ctx.needs_input_grad[1]:
+                    dw = acc_buf if acc_buf is not None else (
+                        st.dw_out if st.dw_out is not None else torch.empty((K, D), device=dev, dtype=torch.float32))
+                    check(_gemm("dw", lambda: L.som_backward_dw(
+                        r_hi, r_lo, ctx.ldr, st.xs.hi, st.xs.lo, st.xs.ld, ptr(st.W), st.W.stride(0), col_part, ncp,
+                        st.ws.aux, ptr(g), B, K, D, mode, ptr(dw), dw.stride(0), 1 if acc_buf is not None else 0, 0,
+                        gws, gws_n, sp)), "som_backward_dw")
+                    if acc_buf is not None:
+                        dw = None
+                    elif hook is not None:
+                        join = hook.exchange_after(dw)      # runs beside the dx GEMM below
+                if ctx.needs_input_grad[0]:
+                    dx = st.dx_out if st.dx_out is not None else torch.empty((B, D), device=dev, dtype=torch.float32)
+                    check(_gemm("dx", lambda: L.som_backward_dx(
+                        r_hi, r_lo, ctx.ldr, st.ws.hi, st.ws.lo, st.ws.ld, ptr(st.x), st.x.stride(0), row_part, nrp,
+                        st.xs.aux, ptr(g), B, K, D, mode, ptr(dx), dx.stride(0), 0, sm_limit if join is not None else 0,
+                        gws, gws_n, sp)), "som_backward_dx")
+            if dx is not None:
+                if dx.dtype != ctx.x_dtype:
+                    dx = dx.to(ctx.x_dtype)
+                dx = dx.view(ctx.x_shape)
+            if join is not None:
+                join()                          # compute stream waits for the communication stream
+        return (dx, dw) + nothing
 
 
 class WeightedLossFn(torch.autograd.Function):
@@ -294,12 +362,15 @@ class WeightedLossFn(torch.autograd.Function):
     def forward(ctx, dist, bmu, grid_pos, T_dev, inv_count, k_offset):
         dist_c = _rowmajor(_require_cuda_f32(dist, "distances"))
         B, K = dist_c.shape
-        loss = torch.empty((), device=dist_c.device, dtype=torch.float32)
+        dev = dist_c.device
+        grid_pos = _grid_f32(grid_pos, dev)
+        loss = torch.empty((), device=dev, dtype=torch.float32)
         L = _lib.lib()
-        scratch = _loss_scratch(dist_c.device, int(L.som_loss_scratch_floats(B, K)))
-        check(L.som_weighted_loss(ptr(dist_c), dist_c.stride(0), ptr(bmu), ptr(grid_pos), B, K, k_offset,
-                                  ptr(T_dev), inv_count, ptr(scratch), ptr(loss), stream_ptr()),
-              "som_weighted_loss")
+        with _guard(dev):
+            scratch = _loss_scratch(dev, int(L.som_loss_scratch_floats(B, K)))
+            check(L.som_weighted_loss(ptr(dist_c), dist_c.stride(0), ptr(bmu), ptr(grid_pos), B, K, k_offset,
+                                      ptr(T_dev), inv_count, ptr(scratch), ptr(loss), stream_ptr(dev)),
+                  "som_weighted_loss")
         ctx.save_for_backward(bmu, grid_pos, T_dev)
         ctx.shape = (B, K)
         ctx.inv_count = inv_count
@@ -310,11 +381,14 @@ class WeightedLossFn(torch.autograd.Function):
     def backward(ctx, g_out):
         bmu, grid_pos, T_dev = ctx.saved_tensors
         B, K = ctx.shape
+        dev = bmu.device
         g = _grad_scalar(g_out)
         ldg = _pad4(K)
-        G = torch.empty((B, ldg), device=g.device, dtype=torch.float32)
-        check(_lib.lib().som_weighted_loss_grad(ptr(bmu), ptr(grid_pos), B, K, ctx.k_offset, ptr(T_dev), ptr(g),
-                                                ctx.inv_count, ptr(G), ldg, stream_ptr()), "som_weighted_loss_grad")
+        G = torch.empty((B, ldg), device=dev, dtype=torch.float32)
+        with _guard(dev):
+            check(_lib.lib().som_weighted_loss_grad(ptr(bmu), ptr(grid_pos), B, K, ctx.k_offset, ptr(T_dev), ptr(g),
+                                                    ctx.inv_count, ptr(G), ldg, stream_ptr(dev)),
+                  "som_weighted_loss_grad")
         return G[:, :K], None, None, None, None, None
 
 
@@ -342,22 +416,23 @@ class DistanceFn(torch.autograd.Function):
         r_lo = torch.empty((B, ldr), device=dev, dtype=torch.float32)
         coef = torch.zeros((2 * B + 2 * K,), device=dev, dtype=torch.float32)
         ax, bx, aw, bw = coef[:B], coef[B:2 * B], coef[2 * B:2 * B + K], coef[2 * B + K:]
-        check(L.som_bwd_coeffs(ptr(G), G.stride(0), ptr(st.dist_buf), st.ldd, B, K, mode, st.xs.aux, st.ws.aux,
-                               ptr(r_hi), ptr(r_lo), ldr, ptr(ax), ptr(bx), ptr(aw), ptr(bw), stream_ptr()),
-              "som_bwd_coeffs")
         dx = dw = None
-        gws, gws_n = gemm_workspace(dev)
-        if ctx.needs_input_grad[0]:
-            dx = torch.empty((B, D), device=dev, dtype=torch.float32)
-            check(_gemm("dx", lambda: L.som_bwd_dx(ptr(r_hi), ptr(r_lo), ldr, st.ws.hi, st.ws.lo, st.ws.ld, ptr(st.x),
-                                                   st.x.stride(0), ptr(ax), ptr(bx), B, K, D, ptr(dx), D,
-                                                   gws, gws_n, stream_ptr())), "som_bwd_dx")
-            if dx.dtype != ctx.x_dtype:
-                dx = dx.to(ctx.x_dtype)
-            dx = dx.view(ctx.x_shape)
-        if ctx.needs_input_grad[1]:
-            dw = torch.empty((K, D), device=dev, dtype=torch.float32)
-            check(_gemm("dw", lambda: L.som_bwd_dw(ptr(r_hi), ptr(r_lo), ldr, st.xs.hi, st.xs.lo, st.xs.ld, ptr(st.W),
-                                                   st.W.stride(0), ptr(aw), ptr(bw), B, K, D, ptr(dw), D,
-                                                   gws, gws_n, stream_ptr())), "som_bwd_dw")
+        with _guard(dev):
+            sp = stream_ptr(dev)
+            check(L.som_bwd_coeffs(ptr(G), G.stride(0), ptr(st.dist_buf), st.ldd, B, K, mode, st.xs.aux, st.ws.aux,
+                                   ptr(r_hi), ptr(r_lo), ldr, ptr(ax), ptr(bx), ptr(aw), ptr(bw), sp), "som_bwd_coeffs")
+            gws, gws_n = gemm_workspace(dev)
+            if ctx.needs_input_grad[0]:
+                dx = torch.empty((B, D), device=dev, dtype=torch.float32)
+                check(_gemm("dx", lambda: L.som_bwd_dx(ptr(r_hi), ptr(r_lo), ldr, st.ws.hi, st.ws.lo, st.ws.ld, ptr(st.x),
+                                                       st.x.stride(0), ptr(ax), ptr(bx), B, K, D, ptr(dx), D,
+                                                       gws, gws_n, sp)), "som_bwd_dx")
+                if dx.dtype != ctx.x_dtype:
+                    dx = dx.to(ctx.x_dtype)
+                dx = dx.view(ctx.x_shape)
+            if ctx.needs_input_grad[1]:
+                dw = torch.empty((K, D), device=dev, dtype=torch.float32)
+                check(_gemm("dw", lambda: L.som_bwd_dw(ptr(r_hi), ptr(r_lo), ldr, st.xs.hi, st.xs.lo, st.xs.ld, ptr(st.W),
+                                                       st.W.stride(0), ptr(aw), ptr(bw), B, K, D, ptr(dw), D,
+                                                       gws, gws_n, sp)), "som_bwd_dw")
         return dx, dw, None

@@ -142,15 +142,35 @@ class SOMLayer(_Base):
                 "B200 hot path; use 'euclidean' or 'cosine'")
         return ops.MODE[self.distance_fcn]
 
-    def _staged_prototypes(self, mode: int):
-        """(staging, needs_refill): tf32 hi/lo split (+ norms) of the prototypes, refilled only when the parameter
-        changed (optimizer step, load_state_dict, .to()).  A fresh buffer is used on every refill so that a
-        backward still holding the previous staging is not overwritten."""
+    def _staging_key(self, mode: int):
         W = self.prototypes
-        key = (W.data_ptr(), W._version, mode, tuple(W.shape), W.device)
+        return (W.data_ptr(), W._version, mode, tuple(W.shape), W.device)
+
+    def invalidate_staging(self):
+        """Forget the cached tf32 staging of the prototypes.  The cache follows the parameter's version counter, which
+        every in-place torch op on the parameter advances (optimizer steps, ``copy_``, ``load_state_dict``) - but writes
+        through ``prototypes.data`` (or through a raw pointer) do not: call this after such a write."""
+        self._w_cache = None
+
+    def _staged_prototypes(self, mode: int):
+        """(staging, needs_refill): tf32 hi/lo split (+ norms) of the prototypes.
+
+        * training mode with gradients enabled: the prototypes change every step, so the staging is part of the step
+          (always refilled) - unless the fused optimizer (``vit_som_b200.FusedPrototypeAdamW``) produced the staging of
+          the current parameter version in its own pass;
+        * under CUDA-graph capture: always refilled (a replay cannot re-run this Python check, and a captured
+          ``stage_w = 0`` would freeze the prototypes of capture time) - again unless the optimizer owns the staging;
+        * eval / no_grad: refilled only when the parameter changed (version counter, ``invalidate_staging``).
+        A fresh buffer is used on every refill so that a backward still holding the previous staging is not overwritten."""
+        key = self._staging_key(mode)
         ws = self._w_cache
         if ws is not None and ws.key == key:
-            return ws, False
+            if ws.from_optimizer:
+                return ws, False
+            volatile = (self.training and torch.is_grad_enabled()) or torch.cuda.is_current_stream_capturing()
+            if not volatile:
+                return ws, False
+        W = self.prototypes
         ws = ops.Staging(W.shape[0], W.shape[1], mode, W.device)
         ws.key = key
         self._w_cache = ws
@@ -168,7 +188,7 @@ class SOMLayer(_Base):
         try:
             state, bmu = ops.forward(x, self.prototypes, mode, ws, refill, want_dist=want_dist)
         except Exception:
-            self._w_cache = None                         # never keep a staging that may not have been filled
+            self.invalidate_staging()                    # never keep a staging that may not have been filled
             raise
         if not want_dist:
             return None, bmu
@@ -237,6 +257,16 @@ class SOMLayer(_Base):
                                             1.0 / (B * K), 0)
         dense = weights.materialize() if isinstance(weights, NeighbourhoodWeights) else weights
         return torch.mean(dense * distances)             # caller supplied its own weights: plain composition
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self.invalidate_staging()
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)        # .to() / .cuda() / .float(): new storage, new staging
+        self.invalidate_staging()
+        self._t_cache = None
+        return out
 
     # ---- the reference's own (dead) Lightning hooks, kept for API completeness -------------------
     def training_step(self, batch, batch_idx):
