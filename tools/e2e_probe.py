@@ -40,7 +40,7 @@ print(f"H2D {xh.numel() * 4 / 1e6:.1f} MB pinned: {ms_copy * 1e3:.1f} us  ({xh.n
 
 
 def step():
-    layer._w_cache = None
+    layer.invalidate_staging()
     layer.prototypes.grad = None
     xd.grad = None
     d, bmu = layer(xd)

@@ -65,9 +65,10 @@ def main():
     dist = torch.empty(B, ldd, device="cuda")
     packed = torch.empty(B, dtype=torch.int64, device="cuda")
     bmu = torch.empty(B, dtype=torch.int64, device="cuda")
-    rbuf = torch.empty(2 * B * ldd + B + K, device="cuda")
+    nrp, ncp = ops.loss_parts(B, K, x.device)                  # partial-sum tables of the loss kernel
+    rbuf = torch.empty(2 * B * ldd + B * nrp + ncp * K, device="cuda")
     r_hi, r_lo = rbuf.data_ptr(), rbuf.data_ptr() + 4 * B * ldd
-    row_sum, col_sum = rbuf.data_ptr() + 8 * B * ldd, rbuf.data_ptr() + 8 * B * ldd + 4 * B
+    row_sum, col_sum = rbuf.data_ptr() + 8 * B * ldd, rbuf.data_ptr() + 8 * B * ldd + 4 * B * nrp
     loss = torch.empty((), device="cuda")
     scratch = torch.zeros(1 << 16, device="cuda")
     dx, dw = torch.empty(B, D, device="cuda"), torch.empty(K, D, device="cuda")
@@ -101,15 +102,24 @@ def main():
         T.data_ptr(), 1.0 / (B * K), mode, r_hi, r_lo,
         ldd, row_sum, col_sum, scratch.data_ptr(), loss.data_ptr(), sp()), "loss"))
     total += timed("GEMM dW", lambda: chk(L.som_backward_dw(
-        r_hi, r_lo, ldd, xs.hi, xs.lo, xs.ld, W.data_ptr(), D, col_sum, ws.aux, g.data_ptr(), B, K, D, mode,
-        dw.data_ptr(), D, 0, wsp, wsn, sp()), "dw"), stamps=True)
+        r_hi, r_lo, ldd, xs.hi, xs.lo, xs.ld, W.data_ptr(), D, col_sum, ncp, ws.aux, g.data_ptr(), B, K, D, mode,
+        dw.data_ptr(), D, 0, 0, wsp, wsn, sp()), "dw"), stamps=True)
     total += timed("GEMM dx", lambda: chk(L.som_backward_dx(
-        r_hi, r_lo, ldd, ws.hi, ws.lo, ws.ld, x.data_ptr(), D, row_sum, xs.aux, g.data_ptr(), B, K, D, mode,
-        dx.data_ptr(), D, 0, wsp, wsn, sp()), "dx"), stamps=True)
+        r_hi, r_lo, ldd, ws.hi, ws.lo, ws.ld, x.data_ptr(), D, row_sum, nrp, xs.aux, g.data_ptr(), B, K, D, mode,
+        dx.data_ptr(), D, 0, 0, wsp, wsn, sp()), "dx"), stamps=True)
     timed("GEMM dW+dx fused launch", lambda: chk(L.som_backward_fused(
-        r_hi, r_lo, ldd, xs.hi, xs.lo, ws.hi, ws.lo, xs.ld, x.data_ptr(), D, W.data_ptr(), D, row_sum, col_sum,
-        xs.aux, ws.aux, g.data_ptr(), B, K, D, mode, dw.data_ptr(), D, 0, dx.data_ptr(), D, wsp, wsn, sp()), "bwd"),
-        stamps=True)
+        r_hi, r_lo, ldd, xs.hi, xs.lo, ws.hi, ws.lo, xs.ld, x.data_ptr(), D, W.data_ptr(), D, row_sum, nrp, col_sum,
+        ncp, xs.aux, ws.aux, g.data_ptr(), B, K, D, mode, dw.data_ptr(), D, 0, dx.data_ptr(), D, 0, None, None,
+        wsp, wsn, sp()), "bwd"), stamps=True)
+    # the fused prototype optimizer step (update + staging): 9 arrays of K x D floats through HBM
+    m, v = torch.zeros_like(W), torch.zeros_like(W)
+    hp = torch.tensor([1e-3, 1.0, 1.0], device="cuda")
+    t_adam = timed("AdamW + W staging", lambda: chk(L.som_adamw_step(
+        W.data_ptr(), D, dw.data_ptr(), D, m.data_ptr(), v.data_ptr(), D, K, D, hp.data_ptr(), 0.9, 0.999, 1e-8, 0.01,
+        mode, ws.hi, ws.lo, ws.ld, ws.aux, sp()), "adamw"))
+    print(f"   AdamW pass: {9 * K * D * 4 / t_adam / 1e3:.0f} GB/s (9 K D floats; L2-warm)")
+    t_loss = 12.0 * B * K
+    print(f"   (loss kernel moves 12 B per element: {t_loss / 1e6:.1f} MB)")
     print(f"sum of step kernels: {total:.1f} us  (B={B} K={K} D={D} {fcn}, workspace={'yes' if use_ws else 'no'})")
 
 

@@ -91,9 +91,14 @@ class DataParallelSOM:
     stream before backward returns dW to autograd.  The local loss is the mean over the local rows, as under DDP."""
 
     def __init__(self, layer: SOMLayer, group=None, broadcast: bool = True, gemm_sm_limit: int | None = None,
-                 nvls: bool | None = None):
+                 nvls: bool | None = None, overlap: str = "counter"):
         if not dist.is_initialized():
             raise SomError("DataParallelSOM needs an initialised torch.distributed process group")
+        if overlap not in ("counter", "split", "after"):
+            raise ValueError("overlap must be 'counter' (fused backward, exchange started by the dW-complete counter), "
+                             "'split' (dW launch -> exchange beside a separate dx launch) or 'after' (fused backward, "
+                             "exchange after it)")
+        self.overlap = overlap
         self.layer, self.group = layer, group
         self.nvls = None
         dev = layer.prototypes.device
@@ -155,7 +160,7 @@ class DataParallelSOM:
         """Device word the dW epilogues raise; also forks the communication stream off the compute stream (what is
         enqueued on it afterwards is ordered behind everything that precedes the backward launch - and belongs to the
         same CUDA-graph capture)."""
-        if self.comm_stream is None:
+        if self.comm_stream is None or self.overlap != "counter":
             return None
         self.comm_stream.wait_stream(torch.cuda.current_stream(self._counter.device))
         return self._counter.data_ptr()

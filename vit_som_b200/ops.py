@@ -308,7 +308,8 @@ class FusedLossFn(torch.autograd.Function):
         with _guard(dev):
             sp = stream_ptr(dev)
             gws, gws_n = gemm_workspace(dev)
-            if ctx.needs_input_grad[0] and ctx.needs_input_grad[1] and FUSE_BACKWARD:
+            split = hook is not None and getattr(hook, "overlap", "counter") == "split"
+            if ctx.needs_input_grad[0] and ctx.needs_input_grad[1] and FUSE_BACKWARD and not split:
                 # both gradients: ONE persistent launch over the tiles of both GEMMs (dW tiles first)
                 dw = acc_buf if acc_buf is not None else (
                     st.dw_out if st.dw_out is not None else torch.empty((K, D), device=dev, dtype=torch.float32))

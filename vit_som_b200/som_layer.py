@@ -167,7 +167,8 @@ class SOMLayer(_Base):
         if ws is not None and ws.key == key:
             if ws.from_optimizer:
                 return ws, False
-            volatile = (self.training and torch.is_grad_enabled()) or torch.cuda.is_current_stream_capturing()
+            volatile = (self.training and torch.is_grad_enabled()) or (
+                self.prototypes.is_cuda and torch.cuda.is_current_stream_capturing())
             if not volatile:
                 return ws, False
         W = self.prototypes
