@@ -329,8 +329,9 @@ def measure_som(env, name, wl, steps, warmup, sharded=False, with_e2e=False, wit
     x_dev = [x_full[r0:r0 + chunk].clone().requires_grad_(True) for r0 in range(0, B, chunk)]
     del x_full
     chunked = len(x_dev) > 1
-    if chunked:                                # chunked: the dW GEMM epilogue accumulates in place across chunks
+    if chunked:                                # chunked: the dW GEMM epilogue accumulates in place across chunks,
         layer.grad_accumulator = torch.zeros(K_local, D, device=dev)
+        layer.batch_rows = B                   # and every chunk's loss is its share of the mean over the whole batch
 
     dp = None
     dp_mode = None
@@ -354,16 +355,16 @@ def measure_som(env, name, wl, steps, warmup, sharded=False, with_e2e=False, wit
             loss.backward()
             return loss.detach()
         layer.grad_accumulator.zero_()
-        total = None
+        losses = []
         for x in xs:
             x.grad = None
             d, bmu = layer(x)
-            loss = layer.som_loss(layer.compute_weights(bmu), d) * (x.shape[0] / B)
+            loss = layer.som_loss(layer.compute_weights(bmu), d)
             loss.backward()
-            total = loss.detach() if total is None else total + loss.detach()
+            losses.append(loss.detach())
         if dp is not None:
             dp.reduce_accumulator()
-        return total
+        return torch.stack(losses).sum()
 
     for _ in range(W_):
         hot_path(x_dev)
@@ -724,7 +725,7 @@ def measure_vit_som(env, tag, dataset, map_size, batch, steps, warmup):
         if model.classification:
             model.cls_head = DDP(model.cls_head, device_ids=[dev.index])
         dp = DataParallelSOM(som, gemm_sm_limit=136, overlap=env.args.dp_overlap)
-    opt_vit, opt_som = build_optimizers(model)
+    opt_vit, opt_som = build_optimizers(model, capturable=True)
     size, chans = cfg["data"]["input_size"], cfg["data"]["num_channels"]
     img = torch.randn(batch, chans, size, size, device=dev)
     labels = torch.randint(0, max(cfg["data"]["num_classes"], 1), (batch,), device=dev)
@@ -741,10 +742,29 @@ def measure_vit_som(env, tag, dataset, map_size, batch, steps, warmup):
     for _ in range(max(warmup, 3)):
         train_step()
     env.barrier()
+    # One GPU: the whole training step (ViT forward / backward, SOM kernels, both optimizers; ~700 launches) is captured
+    # in a CUDA graph - at these model sizes the eager step is bound by the host.  Data parallel: eager (DDP's bucket
+    # all-reduces and the side-stream exchange of DataParallelSOM are left to their own scheduling).
+    graph = None
+    if world == 1 and not env.args.no_graph:
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=env.compute_stream):
+                graph_loss = train_step()
+            graph.replay()
+            torch.cuda.synchronize(dev)
+        except Exception as exc:  # noqa: BLE001
+            print(f"bench[vit {tag}]: CUDA graph capture failed ({exc!r}); eager step", file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize(dev)
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     for _ in range(steps):
-        loss = train_step()
+        if graph is not None:
+            graph.replay()
+            loss = graph_loss
+        else:
+            loss = train_step()
     e.record()
     env.barrier()
     ms = env.max_over_ranks(s.elapsed_time(e))[0] / steps
@@ -755,7 +775,7 @@ def measure_vit_som(env, tag, dataset, map_size, batch, steps, warmup):
            "img_per_s": batch * world / (ms * 1e-3), "ms_per_step": ms, "steps": steps, "n_gpus": world,
            "precision": "bf16 autocast ViT (SDPA), fp32-accurate (3xTF32) SOM layer, fp32 AdamW",
            "step": "forward + CE/SOM loss (device-side gamma ramp, strided SOM input) + backward + AdamW (ViT) + fused "
-                   "AdamW (prototypes); eager launches (host-bound at small batch)",
+                   "AdamW (prototypes); " + ("one CUDA graph per step" if graph is not None else "eager launches"),
            "parallelism": "single GPU" if world == 1 else
                           f"dp{world}: torch DDP (ViT) + DataParallelSOM ({'NVLS' if dp.nvls is not None else 'NCCL'} "
                           "prototype-gradient exchange inside the SOM backward)",

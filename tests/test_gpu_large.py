@@ -82,9 +82,11 @@ def test_config5_slice_through_grad_accumulator(fcn, cuda_device):
     x = torch.randn(B, D)
     chunks = [x[r0:r0 + chunk].cuda().requires_grad_(True) for r0 in range(0, B, chunk)]
     total, bmus = 0.0, []
+    if fcn == "cosine":
+        layer.batch_rows = B                                  # the layer divides by the rows of the whole batch itself
     for xc in chunks:
         d, bmu = layer(xc)
-        loss = layer.som_loss(layer.compute_weights(bmu), d) * (chunk / B)
+        loss = layer.som_loss(layer.compute_weights(bmu), d) * (1.0 if fcn == "cosine" else chunk / B)
         loss.backward()
         total += loss.item()
         bmus.append(bmu.cpu().numpy())
@@ -103,6 +105,6 @@ def test_config5_slice_through_grad_accumulator(fcn, cuda_device):
     for xc in chunks:
         xc.grad = None
         d, bmu = layer(xc)
-        (layer.som_loss(layer.compute_weights(bmu), d) * (chunk / B)).backward()
+        (layer.som_loss(layer.compute_weights(bmu), d) * (1.0 if fcn == "cosine" else chunk / B)).backward()
     torch.cuda.synchronize()
     assert O.rel_err(layer.grad_accumulator.cpu().numpy(), 2.0 * first.cpu().numpy()) < 2e-7

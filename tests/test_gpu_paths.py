@@ -283,7 +283,7 @@ def test_fused_adamw_matches_torch(fcn, shape, cuda_device):
     assert ours._w_cache is ws                                    # not restaged
     ours.invalidate_staging()
     d_f, b_f = ours(x)
-    assert O.rel_err(d_o.cpu().numpy(), d_f.cpu().numpy()) < 1e-6
+    assert O.rel_err(d_o.detach().cpu().numpy(), d_f.detach().cpu().numpy()) < 1e-6
     assert (b_o != b_f).float().mean().item() < 0.05
 
 

@@ -217,11 +217,20 @@ TileChoice pick_tile(int64_t M, int64_t N, int64_t Kred, int sms, int b_mn, int6
       }
       // tile-aligned split-K: fewer tiles than pairs -> every tile cut into `split` equal pieces, one partial-tile
       // hand-over per piece and no slivers (preferred over even ranges at equal cost: it exchanges less)
-      const int64_t split = tiles > 0 ? std::min<int64_t>(slots / tiles, nkb / 8) : 0;
-      if (split >= 2 && tiles * split <= workers) {
-        const int64_t piece = (nkb + split - 1) / split;
-        const double cost = static_cast<double>(piece) * per_kb_ns(2, bn, static_cast<double>(tiles * split) * 2, panel_loads) +
-                            t_epi + 4000.0 + 2000.0;
+      // The owner adds the other pieces' partial tiles one after the other (~0.7 us each: flag, fetch, add), so a long
+      // reduction over few tiles (config 3: one 128 x 16 tile with 384 k-blocks) wants fewer, longer pieces than the
+      // pairs would allow: the split is the one that minimises  piece time + (split - 1) hand-overs.
+      const int64_t split_max = tiles > 0 ? std::min<int64_t>(slots / tiles, nkb / 8) : 0;
+      int64_t split = 0;
+      double split_cost = 1e300;
+      for (int64_t sp = 2; sp <= split_max && tiles * sp <= workers; ++sp) {
+        const int64_t piece = (nkb + sp - 1) / sp;
+        const double c = static_cast<double>(piece) * per_kb_ns(2, bn, static_cast<double>(tiles * sp) * 2, panel_loads) +
+                         t_epi + 4000.0 + 2000.0 + 700.0 * static_cast<double>(sp - 2);
+        if (c < split_cost) { split_cost = c; split = sp; }
+      }
+      if (split >= 2) {
+        const double cost = split_cost;
         if (cost < best_cost * 1.02) {
           best_cost = std::min(best_cost, cost);
           best = TileChoice{2, bn, static_cast<int>(tiles * split), static_cast<int>(split)};
@@ -231,8 +240,13 @@ TileChoice pick_tile(int64_t M, int64_t N, int64_t Kred, int sms, int b_mn, int6
   };
   if (N <= 16 && !b_mn) consider(1, 16);
   for (int bn : {128, 96, 64, 32}) consider(1, bn);
-  if (M > 128 && sms >= 2)
+  // CTA pairs: 256-row tiles - or, for a short M with a long reduction, split-K over many pairs (the second CTA of a
+  // pair then holds zero-filled rows, but the reduction runs on up to 74 pairs instead of one SM)
+  if (sms >= 2 && M > 128) {
     for (int bn : {256, 192, 128, 64}) consider(2, bn);
+  } else if (sms >= 2 && nkb >= 64 && ws_floats > 0) {
+    for (int bn : {64, 32}) consider(2, bn);
+  }
   if (best_cost >= 1e300) {                       // overrides excluded everything: honour them literally
     best.cg = forced_cg ? forced_cg : 1;
     best.bn = forced_bn ? forced_bn : 128;
@@ -987,15 +1001,19 @@ inline int loss_rows_per_block(int64_t B, int64_t K, int sms) {
 // ----------------------------------------------------------------------------------------------
 struct AdamHyper { double beta1, beta2, eps, weight_decay; };   // doubles, like torch's Python scalars
 
-__global__ void __launch_bounds__(256)
+// GROUP threads cooperate on one row (GROUP = 32: warp per row for short rows, GROUP = 256: block per row).
+template <int GROUP>
+__global__ void __launch_bounds__(256, 2)
 adamw_stage_kernel(float* __restrict__ W, long long ldw, const float* __restrict__ dW, long long lddw,
                    float* __restrict__ m, float* __restrict__ v, long long ldm, long long rows, int dim,
                    const float* __restrict__ hp_dev, AdamHyper hp, int mode,
                    float* __restrict__ hi, float* __restrict__ lo, long long ld_out, float* __restrict__ aux) {
   som::pdl_wait();
   som::pdl_launch_dependents();
-  const long long row = blockIdx.x;
-  if (row >= rows) return;
+  constexpr int ROWS_PER_BLOCK = 256 / GROUP;
+  const int gi = threadIdx.x / GROUP, gt = threadIdx.x % GROUP;
+  const long long row = static_cast<long long>(blockIdx.x) * ROWS_PER_BLOCK + gi;
+  const bool active = row < rows;
   const float lr = __ldg(hp_dev), t = __ldg(hp_dev + 1), gscale = __ldg(hp_dev + 2);
   // bias corrections in double like torch's Python scalars (bias_correction2_sqrt = sqrt(1 - beta2^t))
   const double bc1 = 1.0 - pow(hp.beta1, static_cast<double>(t));
@@ -1005,10 +1023,11 @@ adamw_stage_kernel(float* __restrict__ W, long long ldw, const float* __restrict
   const float decay = static_cast<float>(1.0 - static_cast<double>(lr) * hp.weight_decay);
   const float omb1 = static_cast<float>(1.0 - hp.beta1), omb2 = static_cast<float>(1.0 - hp.beta2);
   const float b2 = static_cast<float>(hp.beta2), eps = static_cast<float>(hp.eps);
-  float* wrow = W + row * ldw;
-  const float* grow = dW + row * lddw;
-  float* mrow = m + row * ldm;
-  float* vrow = v + row * ldm;
+  const long long r_ = active ? row : 0;
+  float* wrow = W + r_ * ldw;
+  const float* grow = dW + r_ * lddw;
+  float* mrow = m + r_ * ldm;
+  float* vrow = v + r_ * ldm;
   auto update = [&](float w, float g, float& mm, float& vv) {
     g *= gscale;
     w *= decay;
@@ -1021,50 +1040,81 @@ adamw_stage_kernel(float* __restrict__ W, long long ldw, const float* __restrict
                    ((reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(dW) | reinterpret_cast<uintptr_t>(m) |
                      reinterpret_cast<uintptr_t>(v)) & 15) == 0;
   constexpr int CACHE = 8;
-  const bool cached = vec && dim <= CACHE * 256 * 4;
+  const bool cached = vec && dim <= CACHE * GROUP * 4;      // the new row waits in registers for its norm
   float4 cache[CACHE];
   float ss = 0.f;
-  if (vec) {
+  if (active) {
+    if (cached) {
+      // four row segments at a time: all their loads first (4 arrays x 4 x 16 bytes in flight per thread), then the
+      // arithmetic and the stores
 #pragma unroll
-    for (int j = 0; j < CACHE; ++j) cache[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    int j = 0;
-    for (int i = threadIdx.x * 4; i < dim; i += 256 * 4, ++j) {
-      float4 w4 = *reinterpret_cast<const float4*>(wrow + i);
-      const float4 g4 = __ldg(reinterpret_cast<const float4*>(grow + i));
-      float4 m4 = *reinterpret_cast<const float4*>(mrow + i);
-      float4 v4 = *reinterpret_cast<const float4*>(vrow + i);
-      w4.x = update(w4.x, g4.x, m4.x, v4.x); w4.y = update(w4.y, g4.y, m4.y, v4.y);
-      w4.z = update(w4.z, g4.z, m4.z, v4.z); w4.w = update(w4.w, g4.w, m4.w, v4.w);
-      *reinterpret_cast<float4*>(wrow + i) = w4;
-      *reinterpret_cast<float4*>(mrow + i) = m4;
-      *reinterpret_cast<float4*>(vrow + i) = v4;
-      ss = fmaf(w4.x, w4.x, ss); ss = fmaf(w4.y, w4.y, ss); ss = fmaf(w4.z, w4.z, ss); ss = fmaf(w4.w, w4.w, ss);
-      if (cached) {
+      for (int j0 = 0; j0 < CACHE; j0 += 4) {
+        float4 w4[4], g4[4], m4[4], v4[4];
 #pragma unroll
-        for (int jj = 0; jj < CACHE; ++jj) if (jj == j) cache[jj] = w4;     // static register indices
+        for (int jj = 0; jj < 4; ++jj) {
+          const int i = (gt + (j0 + jj) * GROUP) * 4;
+          if (i < dim) {
+            w4[jj] = *reinterpret_cast<const float4*>(wrow + i);
+            g4[jj] = __ldg(reinterpret_cast<const float4*>(grow + i));
+            m4[jj] = *reinterpret_cast<const float4*>(mrow + i);
+            v4[jj] = *reinterpret_cast<const float4*>(vrow + i);
+          }
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int i = (gt + (j0 + jj) * GROUP) * 4;
+          cache[j0 + jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < dim) {
+            float4 w = w4[jj], mm = m4[jj], vv = v4[jj];
+            const float4 g = g4[jj];
+            w.x = update(w.x, g.x, mm.x, vv.x); w.y = update(w.y, g.y, mm.y, vv.y);
+            w.z = update(w.z, g.z, mm.z, vv.z); w.w = update(w.w, g.w, mm.w, vv.w);
+            *reinterpret_cast<float4*>(wrow + i) = w;
+            *reinterpret_cast<float4*>(mrow + i) = mm;
+            *reinterpret_cast<float4*>(vrow + i) = vv;
+            ss = fmaf(w.x, w.x, ss); ss = fmaf(w.y, w.y, ss); ss = fmaf(w.z, w.z, ss); ss = fmaf(w.w, w.w, ss);
+            cache[j0 + jj] = w;
+          }
+        }
+      }
+    } else if (vec) {
+      for (int i = gt * 4; i < dim; i += GROUP * 4) {
+        float4 w = *reinterpret_cast<const float4*>(wrow + i);
+        const float4 g = __ldg(reinterpret_cast<const float4*>(grow + i));
+        float4 mm = *reinterpret_cast<const float4*>(mrow + i);
+        float4 vv = *reinterpret_cast<const float4*>(vrow + i);
+        w.x = update(w.x, g.x, mm.x, vv.x); w.y = update(w.y, g.y, mm.y, vv.y);
+        w.z = update(w.z, g.z, mm.z, vv.z); w.w = update(w.w, g.w, mm.w, vv.w);
+        *reinterpret_cast<float4*>(wrow + i) = w;
+        *reinterpret_cast<float4*>(mrow + i) = mm;
+        *reinterpret_cast<float4*>(vrow + i) = vv;
+        ss = fmaf(w.x, w.x, ss); ss = fmaf(w.y, w.y, ss); ss = fmaf(w.z, w.z, ss); ss = fmaf(w.w, w.w, ss);
+      }
+    } else {
+      for (int i = gt; i < dim; i += GROUP) {
+        float mm = mrow[i], vv = vrow[i];
+        const float w = update(wrow[i], __ldg(grow + i), mm, vv);
+        wrow[i] = w; mrow[i] = mm; vrow[i] = vv;
+        ss = fmaf(w, w, ss);
       }
     }
-  } else {
-    for (int i = threadIdx.x; i < dim; i += 256) {
-      float mm = mrow[i], vv = vrow[i];
-      const float w = update(wrow[i], __ldg(grow + i), mm, vv);
-      wrow[i] = w; mrow[i] = mm; vrow[i] = vv;
-      ss = fmaf(w, w, ss);
-    }
   }
-  if (!hi) return;                                           // optimizer step only (no staging requested)
-  __shared__ float red[8];
+  if (!hi) return;                                           // optimizer step only (no staging requested): uniform
   ss = warp_sum(ss);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
-  __syncthreads();
-  ss = 0.f;
+  if constexpr (GROUP == 256) {
+    __shared__ float red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    ss = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) ss += red[i];
+    for (int i = 0; i < 8; ++i) ss += red[i];
+  }
+  if (!active) return;
   float denom = 1.f;
   if (mode == 1) {
     denom = fmaxf(sqrtf(ss), 1e-12f);                        // F.normalize(p=2, eps=1e-12), as prep_rows_kernel
-    if (threadIdx.x == 0) aux[row] = 1.f / denom;
-  } else if (threadIdx.x == 0) {
+    if (gt == 0) aux[row] = 1.f / denom;
+  } else if (gt == 0) {
     aux[row] = ss;
   }
   float* ph = hi + row * ld_out;
@@ -1075,25 +1125,29 @@ adamw_stage_kernel(float* __restrict__ W, long long ldw, const float* __restrict
     h = tf32_rna(x);
     l = tf32_rna(x - h);
   };
-  if (vec) {
-    int j = 0;
-    for (int i = threadIdx.x * 4; i < dim_out; i += 256 * 4, ++j) {
-      float4 h = make_float4(0.f, 0.f, 0.f, 0.f), l = h;
-      if (i < dim) {
-        float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (cached) {
+  auto split4 = [&](float4 w, float4& h, float4& l) {
+    split1(w.x, h.x, l.x); split1(w.y, h.y, l.y); split1(w.z, h.z, l.z); split1(w.w, h.w, l.w);
+  };
+  if (cached) {
 #pragma unroll
-          for (int jj = 0; jj < CACHE; ++jj) if (jj == j) w4 = cache[jj];
-        } else {
-          w4 = *reinterpret_cast<const float4*>(wrow + i);   // this thread's own store of the update pass
-        }
-        split1(w4.x, h.x, l.x); split1(w4.y, h.y, l.y); split1(w4.z, h.z, l.z); split1(w4.w, h.w, l.w);
+    for (int j = 0; j < CACHE; ++j) {
+      const int i = (gt + j * GROUP) * 4;
+      if (i < dim_out) {
+        float4 h = make_float4(0.f, 0.f, 0.f, 0.f), l = h;
+        if (i < dim) split4(cache[j], h, l);
+        *reinterpret_cast<float4*>(ph + i) = h;
+        *reinterpret_cast<float4*>(pl + i) = l;
       }
+    }
+  } else if (vec) {
+    for (int i = gt * 4; i < dim_out; i += GROUP * 4) {
+      float4 h = make_float4(0.f, 0.f, 0.f, 0.f), l = h;
+      if (i < dim) split4(*reinterpret_cast<const float4*>(wrow + i), h, l);   // this thread's own store of the update pass
       *reinterpret_cast<float4*>(ph + i) = h;
       *reinterpret_cast<float4*>(pl + i) = l;
     }
   } else {
-    for (int i = threadIdx.x; i < dim_out; i += 256) {
+    for (int i = gt; i < dim_out; i += GROUP) {
       float h = 0.f, l = 0.f;
       if (i < dim) split1(wrow[i], h, l);
       ph[i] = h;
@@ -1580,10 +1634,16 @@ int som_adamw_step(float* W, int64_t ldw, const float* dW, int64_t lddw, float* 
     if (mode != SOM_MODE_EUCLIDEAN && mode != SOM_MODE_COSINE) return fail(SOM_ERR_ARG, "som_adamw_step: bad mode");
   }
   AdamHyper hp{beta1, beta2, eps, weight_decay};
-  SOM_CUDA(launch_kernel(adamw_stage_kernel, dim3(static_cast<unsigned>(K)), dim3(256), 0, as_stream(stream), W,
-                         static_cast<long long>(ldw), dW, static_cast<long long>(lddw), m, v, static_cast<long long>(ldm),
-                         static_cast<long long>(K), static_cast<int>(D), hp_dev, hp, mode, w_hi, w_lo,
-                         static_cast<long long>(ld_stage), w_aux));
+  if (D <= 1024)
+    SOM_CUDA(launch_kernel(adamw_stage_kernel<32>, dim3(static_cast<unsigned>((K + 7) / 8)), dim3(256), 0, as_stream(stream),
+                           W, static_cast<long long>(ldw), dW, static_cast<long long>(lddw), m, v,
+                           static_cast<long long>(ldm), static_cast<long long>(K), static_cast<int>(D), hp_dev, hp, mode,
+                           w_hi, w_lo, static_cast<long long>(ld_stage), w_aux));
+  else
+    SOM_CUDA(launch_kernel(adamw_stage_kernel<256>, dim3(static_cast<unsigned>(K)), dim3(256), 0, as_stream(stream), W,
+                           static_cast<long long>(ldw), dW, static_cast<long long>(lddw), m, v, static_cast<long long>(ldm),
+                           static_cast<long long>(K), static_cast<int>(D), hp_dev, hp, mode, w_hi, w_lo,
+                           static_cast<long long>(ld_stage), w_aux));
   g_launches.fetch_add(1);
   return SOM_OK;
 }

@@ -377,7 +377,7 @@ class PrototypeShardedSOM(SOMLayer):
         if not (isinstance(weights, NeighbourhoodWeights) and weights._dense is None and state is not None):
             raise SomError("PrototypeShardedSOM.som_loss needs the lazy weights of compute_weights() and the "
                            "distances returned by this layer's forward")
-        B = distances.shape[0]
+        B = distances.shape[0] if self.batch_rows is None else int(self.batch_rows)
         want_grad = torch.is_grad_enabled() and (state.x_in.requires_grad or state.W_in.requires_grad)
         return _ShardedLossFn.apply(state.x_in, state.W_in, state, weights.bmu, self.grid_positions, weights.T_dev,
                                     1.0 / (B * self.k_total), self.k_begin, want_grad, self.group,

@@ -115,6 +115,9 @@ class SOMLayer(_Base):
         # optional [K, D] fp32 buffer: when set, backward ADDS the prototype gradient into it from the GEMM epilogue
         # and returns no gradient for `prototypes` to autograd (row-chunked batches accumulate without extra passes)
         self.grad_accumulator = None
+        # optional: rows of the WHOLE batch when it is fed in row chunks - som_loss then divides by batch_rows * K, so
+        # the chunk losses (and their gradients) simply add up to the loss of the whole batch (None: rows of the call)
+        self.batch_rows = None
         self._dw_hook = None                                              # data-parallel wrapper: called with dW as soon as it is enqueued
         self._dw_out = None                                               # data-parallel wrapper: [K, D] buffer the dW GEMM writes (NVLS symmetric memory)
 
@@ -245,19 +248,21 @@ class SOMLayer(_Base):
         return 0, 0
 
     def som_loss(self, weights, distances):
+        B, K = distances.shape
+        rows = B if self.batch_rows is None else int(self.batch_rows)
         if isinstance(weights, NeighbourhoodWeights) and weights._dense is None:
-            B, K = distances.shape
             state = getattr(distances, "_som_state", None)
             if state is not None and state.B == B and state.K == K:
                 # distances are this layer's own forward output: loss and its backward as one node over (x, W)
                 want_grad = torch.is_grad_enabled() and (state.x_in.requires_grad or state.W_in.requires_grad)
                 return ops.FusedLossFn.apply(state.x_in, state.W_in, state, weights.bmu, self.grid_positions,
-                                             weights.T_dev, 1.0 / (B * K), 0, want_grad, self._dw_hook,
+                                             weights.T_dev, 1.0 / (rows * K), 0, want_grad, self._dw_hook,
                                              self._square_grid_dims())
             return ops.WeightedLossFn.apply(distances, weights.bmu, self.grid_positions, weights.T_dev,
-                                            1.0 / (B * K), 0)
+                                            1.0 / (rows * K), 0)
         dense = weights.materialize() if isinstance(weights, NeighbourhoodWeights) else weights
-        return torch.mean(dense * distances)             # caller supplied its own weights: plain composition
+        loss = torch.mean(dense * distances)             # caller supplied its own weights: plain composition
+        return loss if rows == B else loss * (B / rows)
 
     def _load_from_state_dict(self, *args, **kwargs):
         super()._load_from_state_dict(*args, **kwargs)

@@ -158,10 +158,12 @@ class ViTSOM(nn.Module):
         return task + g * som_loss, som_loss.detach()
 
 
-def build_optimizers(model: ViTSOM, fused_prototypes: bool = True):
+def build_optimizers(model: ViTSOM, fused_prototypes: bool = True, capturable: bool = False):
     """AdamW as the reference configures it (models/vit_som.py:126-151): lr = yaml lr * batch / 256, betas from the
     YAML, weight decay on the >= 2-D ViT parameters, the default 0.01 on the SOM prototypes / classification head.
-    Returns (optimizer of the ViT and head, optimizer of the prototypes)."""
+    Returns (optimizer of the ViT and head, optimizer of the prototypes).  ``capturable``: keep the step counts of the
+    ViT optimizer on the device so that the whole training step can be captured in a CUDA graph (the prototype
+    optimizer always is)."""
     hp = model.config["hyperparameters"]
     opt = hp["optimizer"]
     lr = opt["lr"] * hp["batch_size"] / 256
@@ -173,8 +175,8 @@ def build_optimizers(model: ViTSOM, fused_prototypes: bool = True):
         groups.append({"params": list(model.cls_head.parameters())})
     if not fused_prototypes:
         groups.append({"params": list(model.som_layer.parameters())})
-        return torch.optim.AdamW(groups, lr=lr, betas=betas, fused=True), None
-    return (torch.optim.AdamW(groups, lr=lr, betas=betas, fused=True),
+        return torch.optim.AdamW(groups, lr=lr, betas=betas, fused=True, capturable=capturable), None
+    return (torch.optim.AdamW(groups, lr=lr, betas=betas, fused=True, capturable=capturable),
             FusedPrototypeAdamW(model.som_layer, lr=lr, betas=betas))
 
 
