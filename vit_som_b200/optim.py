@@ -54,7 +54,9 @@ class FusedPrototypeAdamW(torch.optim.Optimizer):
         self._hp[1] = float(step.item() if torch.is_tensor(step) else step)
         st["step"] = self._hp[1]                          # the kernel reads the count from the hyper-parameter block
         for k in ("exp_avg", "exp_avg_sq"):
-            st[k] = st[k].to(device=W.device, dtype=torch.float32).contiguous()
+            # private copies: torch's load_state_dict keeps tensors that already have the right dtype and device, so the
+            # moments would alias the buffers of the optimizer the state came from
+            st[k] = st[k].detach().to(device=W.device, dtype=torch.float32).clone(memory_format=torch.contiguous_format)
         self._lr_on_device = None
 
     @torch.no_grad()
