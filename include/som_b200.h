@@ -286,8 +286,10 @@ int som_debug_gemm(const float* a_hi, const float* a_lo, int64_t lda, int a_mn,
                    float* C, int64_t ldc, float* ws, int64_t ws_floats, void* stream);
 
 /* Diagnostics, host only: the work decomposition of the CTA-pair kernel for `workers` CTA pairs over the k-block units
- * of one or two GEMMs (tiles x k-blocks each; tiles1 = 0 for one GEMM).  split > 0: tile-aligned split-K, else even
- * ranges (stream-K).  bounds_out[0..workers]: first unit of every worker, then the total. */
+ * of one or two GEMMs (tiles x k-blocks each; tiles1 = 0 for one GEMM).  split > 0: tile-aligned split-K, 0: even
+ * ranges (stream-K).  bounds_out[0..workers]: first unit of every worker, then the total.  split < 0: the two-phase
+ * schedule of the data-parallel backward (every worker: its share of GEMM 0, then its share of GEMM 1);
+ * bounds_out[0..workers] = phase 0, bounds_out[workers+1 .. 2 workers+1] = phase 1. */
 int som_debug_schedule(int64_t tiles0, int64_t nkb0, int64_t tiles1, int64_t nkb1, int workers, int split,
                        int64_t* bounds_out);
 

@@ -115,7 +115,7 @@ def test_integration_doc_cpp_stub_matches_the_header():
 
 def test_abi_version_and_pure_host_entry_points(lib):
     assert lib.som_b200_abi_version() == 6
-    assert lib.som_gemm_workspace_floats() == 4096 + 74 * 256 * 256      # 74 CTA pairs: a B200, and the GPU-less default
+    assert lib.som_gemm_workspace_floats() == 4096 + 2 * 74 * 256 * 256  # 74 CTA pairs (a B200, and the GPU-less default), two slots each
     assert lib.som_loss_scratch_floats(1024, 1600) >= 1024 * 2
     assert lib.som_loss_fused_scratch_floats(1024, 1600) == (1024 // 8) * 4 + 2
     lib.som_launch_count_reset()
@@ -193,3 +193,27 @@ def test_every_worker_of_a_cut_tile_has_work(lib):
             continue
         b = _bounds(lib, tiles, nkb, 0, 0, tiles * split, split)
         assert all(y - x >= 1 for x, y in zip(b, b[1:]))
+
+
+def test_two_phase_schedule_partitions_both_gemms(lib):
+    """Data-parallel backward: every worker gets an even share of GEMM 0 (dW) and then an even share of GEMM 1 (dx);
+    each phase covers its GEMM exactly once, in order, and no share is empty when there are at least as many units as
+    workers (the hand-over invariant of the in-kernel reduction, per phase)."""
+    import random
+    rng = random.Random(2)
+    for _ in range(200):
+        tiles0, nkb0 = rng.randint(1, 300), rng.randint(1, 200)
+        tiles1, nkb1 = rng.randint(1, 300), rng.randint(1, 200)
+        workers = rng.randint(2, 74)
+        out = (ctypes.c_int64 * (2 * (workers + 1)))()
+        assert lib.som_debug_schedule(tiles0, nkb0, tiles1, nkb1, workers, -1, out) == 0
+        b = list(out)
+        ph0, ph1 = b[:workers + 1], b[workers + 1:]
+        u0, u1 = tiles0 * nkb0, tiles1 * nkb1
+        assert ph0[0] == 0 and ph0[-1] == u0 and ph1[0] == u0 and ph1[-1] == u0 + u1
+        for ph, units in ((ph0, u0), (ph1, u1)):
+            sizes = [y - x for x, y in zip(ph, ph[1:])]
+            assert all(sz >= 0 for sz in sizes) and max(sizes) - min(sizes) <= 1
+            assert units < workers or min(sizes) >= 1
+    out = (ctypes.c_int64 * 8)()
+    assert lib.som_debug_schedule(4, 8, 0, 0, 3, -1, out) != 0          # needs two GEMMs

@@ -164,10 +164,10 @@ double per_kb_ns(int cg, int bn, double active_sms, bool mn_major = false) {
   return std::max(4.43 * bn, t_l2);
 }
 // Stream-K workers for `units` k-block units of 256 x bn pair tiles (0 = do not use stream-K).
-int64_t streamk_workers(int64_t units, int64_t slots, int bn, int64_t ws_floats) {
+int64_t streamk_workers(int64_t units, int64_t slots, int bn, int64_t ws_floats, int phases = 1) {
   int64_t workers = std::min<int64_t>(slots, std::max<int64_t>(1, units / 4));
-  workers = std::min<int64_t>(workers, (ws_floats - SK_FLAG_WORDS) / (256 * static_cast<int64_t>(bn)));
-  workers = std::min<int64_t>(workers, SK_FLAG_WORDS / 16);
+  workers = std::min<int64_t>(workers, (ws_floats - SK_FLAG_WORDS) / (phases * 256 * static_cast<int64_t>(bn)));
+  workers = std::min<int64_t>(workers, SK_FLAG_WORDS / (16 * phases));
   return workers >= 2 ? workers : 0;
 }
 double streamk_cost_ns(int64_t units, int64_t workers, int64_t nkb_typ, int bn, bool mn_major) {
@@ -1265,10 +1265,11 @@ void som_set_debug_times(unsigned long long* dev_buf) { g_dbg_times.store(dev_bu
 void som_set_pdl(int on) { g_pdl.store(on ? 1 : 0); }
 void som_set_streamk(int mode) { g_streamk.store(mode < 0 ? -1 : (mode > 0 ? 1 : 0)); }
 int64_t som_gemm_workspace_floats(void) {
-  // one 256 x 256 partial tile per CTA pair of the current device (148 SMs -> 74 pairs on a B200)
+  // 256 x 256 partial tiles for every CTA pair of the current device (148 SMs -> 74 pairs on a B200)
   DeviceInfo di;
   const int64_t pairs = device_info(di) == SOM_OK && di.sms >= 2 ? di.sms / 2 : 74;
-  return SK_FLAG_WORDS + std::min<int64_t>(pairs, SK_FLAG_WORDS / 16) * 256 * 256;
+  // (two slots per pair: the two-phase schedule of the data-parallel backward hands over one partial tile per phase)
+  return SK_FLAG_WORDS + 2 * std::min<int64_t>(pairs, SK_FLAG_WORDS / 32) * 256 * 256;
 }
 void som_set_cta_group(int cg) { g_cg_override.store(cg == 1 || cg == 2 ? cg : 0); }
 
@@ -1549,16 +1550,22 @@ int som_backward_fused(const float* r_hi, const float* r_lo, int64_t ldr, const 
   const int forced_bn = g_bn_override.load();
   const int64_t slots = sms / 2;
   int best_bn = 0; int64_t best_workers = 0; double best_cost = 1e300;
+  // Data parallel (dw_done): two-phase schedule - every pair first works off its share of the dW tiles, then its share
+  // of the dx tiles, so dW is complete (and its exchange can start) after about half of the launch.
+  const bool phased = dw_done != nullptr;
   if (ws && g_streamk.load() >= 0 && g_cg_override.load() != 1 && B > 128 && K > 128) {
     for (int bn : {256, 192, 128, 64}) {
       if (forced_bn && bn != forced_bn) continue;
-      int64_t units = 0, nkb_max = 1;
+      int64_t units = 0, nkb_max = 1, units_min = INT64_MAX;
       for (int i = 0; i < 2; ++i) {
         const int64_t nkb = (p[i].Kred + som::BK - 1) / som::BK;
-        units += ((p[i].M + 255) / 256) * ((p[i].N + bn - 1) / bn) * nkb;
+        const int64_t u = ((p[i].M + 255) / 256) * ((p[i].N + bn - 1) / bn) * nkb;
+        units += u;
+        units_min = std::min(units_min, u);
         nkb_max = std::max(nkb_max, nkb);
       }
-      const int64_t workers = streamk_workers(units, slots, bn, ws_floats);
+      const int64_t workers = phased ? streamk_workers(2 * units_min, slots, bn, ws_floats, 2)
+                                     : streamk_workers(units, slots, bn, ws_floats);
       if (workers < 2) continue;
       const bool panel_loads = D % 32 != 0 || (bn / 2) % 32 != 0 || !g_tma3d.load();    // B of both GEMMs has extent D
       const double cost = streamk_cost_ns(units, workers, nkb_max, bn, panel_loads);
@@ -1577,8 +1584,8 @@ int som_backward_fused(const float* r_hi, const float* r_lo, int64_t ldr, const 
     // 16 warp slabs (2 CTAs x 8 epilogue warps) per 256 x bn tile of dW, each counted once by the tile's owner
     if (dw_done_expected) *dw_done_expected = ((K + 255) / 256) * ((D + best_bn - 1) / best_bn) * 16;
   }
-  return launch_pair(som::EPI_GRAD, p, 2, best_bn, static_cast<int>(best_workers), 0, pair_kchunk(g_kchunk.load(), 3),
-                     3, ws, sms, as_stream(stream));
+  return launch_pair(som::EPI_GRAD, p, 2, best_bn, static_cast<int>(best_workers), phased ? -1 : 0,
+                     pair_kchunk(g_kchunk.load(), 3), 3, ws, sms, as_stream(stream));
 }
 
 // ---- stream-ordered memory operations (driver API cuStreamWaitValue32 / cuStreamWriteValue32) ---------------------
@@ -1684,6 +1691,12 @@ int som_debug_schedule(int64_t tiles0, int64_t nkb0, int64_t tiles1, int64_t nkb
   s.units0 = tiles0 * nkb0;
   s.units = s.units0 + tiles1 * (tiles1 > 0 ? nkb1 : 0);
   s.split = split;
+  if (split < 0) {                                  // two-phase schedule: phase-0 bounds, then phase-1 bounds
+    if (tiles1 <= 0) return fail(SOM_ERR_ARG, "som_debug_schedule: the two-phase schedule needs two GEMMs");
+    for (int ph = 0; ph < 2; ++ph)
+      for (int p = 0; p <= workers; ++p) bounds_out[ph * (workers + 1) + p] = som::sk_bound_phase(s, workers, p, ph);
+    return SOM_OK;
+  }
   for (int p = 0; p <= workers; ++p) bounds_out[p] = som::sk_bound(s, workers, p);
   return SOM_OK;
 }
