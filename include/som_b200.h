@@ -266,10 +266,13 @@ int som_adamw_step(float* W, int64_t ldw, const float* dW, int64_t lddw, float* 
  *   flag_ptrs device array of `world` pointers to the ranks' zero-initialised flag buffers (peer mapped), each of at
  *             least som_nvls_flag_words(world) 32-bit words; the kernel leaves them zero again
  *   n_floats  multiple of 4.   Every rank of the group must make the call.
+ *   blocks    grid size (512 threads each, two per SM; <= 64, the same on every rank): the kernel is bound by the bytes
+ *             it keeps in flight, so give it two blocks per SM that is free - 2 x (SMs - sm_limit) beside a GEMM.
  */
-int som_allreduce_mean_nvls(float* mc_ptr, void* flag_ptrs, int64_t n_floats, int rank, int world, void* stream);
+int som_allreduce_mean_nvls(float* mc_ptr, void* flag_ptrs, int64_t n_floats, int rank, int world, int blocks, void* stream);
 /* The same kernel with an explicit factor (1.0f = SUM): the partial dx[B,D] of prototype shards. */
-int som_allreduce_nvls(float* mc_ptr, void* flag_ptrs, int64_t n_floats, int rank, int world, float scale, void* stream);
+int som_allreduce_nvls(float* mc_ptr, void* flag_ptrs, int64_t n_floats, int rank, int world, float scale, int blocks,
+                       void* stream);
 int64_t som_nvls_flag_words(int world);
 
 /*

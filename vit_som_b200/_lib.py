@@ -70,8 +70,8 @@ SIGNATURES = {
     "som_stream_write_value": (c_int, [_P, c_uint32, _P]),
     "som_adamw_step": (c_int, [_P, c_int64, _P, c_int64, _P, _P, c_int64, c_int64, c_int64, _P, c_double, c_double,
                                c_double, c_double, c_int, _P, _P, c_int64, _P, _P]),
-    "som_allreduce_mean_nvls": (c_int, [_P, _P, c_int64, c_int, c_int, _P]),
-    "som_allreduce_nvls": (c_int, [_P, _P, c_int64, c_int, c_int, c_float, _P]),
+    "som_allreduce_mean_nvls": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, _P]),
+    "som_allreduce_nvls": (c_int, [_P, _P, c_int64, c_int, c_int, c_float, c_int, _P]),
     "som_nvls_flag_words": (c_int64, [c_int]),
     "som_debug_schedule": (c_int, [c_int64, c_int64, c_int64, c_int64, c_int, c_int, _P]),
     "som_debug_gemm": (c_int, [_P, _P, c_int64, c_int, _P, _P, c_int64, c_int, c_int64, c_int64, c_int64,

@@ -1167,9 +1167,12 @@ adamw_stage_kernel(float* __restrict__ W, long long ldw, const float* __restrict
 // flag[b][r] in every peer's copy (CAS 0 -> 1, release.sys) and lowers its own copy's flag[b][peer] (CAS 1 -> 0,
 // acquire.sys): self-resetting, so launches (and CUDA-graph replays) can follow each other without host involvement.
 // ----------------------------------------------------------------------------------------------
-// 16 blocks at two per SM: the kernel fits beside a GEMM that leaves 8+ SMs free (with more blocks than free SMs the
-// late ones would only start after the GEMM, and the exchange would finish after it instead of under it)
-constexpr int NVLS_BLOCKS = 16;
+// Two blocks per SM: beside a GEMM the grid is twice the number of SMs the GEMM leaves free (with more blocks than free
+// SMs the late ones would only start after the GEMM, and the exchange would finish after it instead of under it).
+// Measured (2 GPUs, 20 MB): 16 blocks keep ~1 MB in flight per GPU and need 75 us - latency bound, NVLink is idle.
+constexpr int NVLS_MAX_BLOCKS = 64;      // flag buffers are sized for this many barrier channels; the caller picks the grid:
+                                         // two blocks per SM the GEMM beside it leaves free (24 for 136 of 148 SMs), more
+                                         // when nothing runs concurrently (the kernel is bound by the bytes it keeps in flight)
 constexpr int NVLS_UNROLL = 8;
 constexpr int NVLS_THREADS = 512;
 
@@ -1661,22 +1664,26 @@ int som_adamw_step(float* W, int64_t ldw, const float* dW, int64_t lddw, float* 
 //               som_nvls_flag_words(world) 32-bit words (peer-mapped symmetric allocation)
 //   n_floats  : multiple of 4
 // Must be launched by every rank of the group (it contains cross-GPU barriers); enqueues one kernel on `stream`.
-int som_allreduce_nvls(float* mc_ptr, void* flag_ptrs, int64_t n_floats, int rank, int world, float scale, void* stream) {
+int som_allreduce_nvls(float* mc_ptr, void* flag_ptrs, int64_t n_floats, int rank, int world, float scale, int blocks,
+                       void* stream) {
   DeviceInfo di;
   if (int rc = device_info(di)) return rc;
   if (!mc_ptr || !flag_ptrs || n_floats <= 0 || (n_floats & 3) != 0 || world < 1 || world > 32 || rank < 0 || rank >= world)
     return fail(SOM_ERR_ARG, "som_allreduce_nvls: bad argument");
   if ((reinterpret_cast<uintptr_t>(mc_ptr) & 15) != 0) return fail(SOM_ERR_ARG, "som_allreduce_nvls: misaligned buffer");
-  nvls_allreduce_mean_kernel<<<NVLS_BLOCKS, NVLS_THREADS, 0, as_stream(stream)>>>(
+  if (blocks <= 0) blocks = 16;
+  if (blocks > NVLS_MAX_BLOCKS) blocks = NVLS_MAX_BLOCKS;          // every rank must pass the same value
+  nvls_allreduce_mean_kernel<<<blocks, NVLS_THREADS, 0, as_stream(stream)>>>(
       mc_ptr, reinterpret_cast<unsigned int* const*>(flag_ptrs), n_floats / 4, rank, world, scale);
   SOM_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
   return SOM_OK;
 }
-int som_allreduce_mean_nvls(float* mc_ptr, void* flag_ptrs, int64_t n_floats, int rank, int world, void* stream) {
-  return som_allreduce_nvls(mc_ptr, flag_ptrs, n_floats, rank, world, 1.0f / static_cast<float>(world > 0 ? world : 1), stream);
+int som_allreduce_mean_nvls(float* mc_ptr, void* flag_ptrs, int64_t n_floats, int rank, int world, int blocks, void* stream) {
+  return som_allreduce_nvls(mc_ptr, flag_ptrs, n_floats, rank, world, 1.0f / static_cast<float>(world > 0 ? world : 1), blocks,
+                            stream);
 }
-int64_t som_nvls_flag_words(int world) { return static_cast<int64_t>(NVLS_BLOCKS) * (world > 0 ? world : 1); }
+int64_t som_nvls_flag_words(int world) { return static_cast<int64_t>(NVLS_MAX_BLOCKS) * (world > 0 ? world : 1); }
 
 // Host-side view of the CTA-pair kernel's work decomposition (the same sk_bound() the device code evaluates):
 // bounds_out[p] = first k-block unit of worker p, bounds_out[workers] = total units.  Pure host code (tests).

@@ -108,6 +108,12 @@ class DataParallelSOM:
         # lowest priority: when the exchange and GEMM tiles become runnable together the GEMM's CTA pairs are placed first
         self.comm_stream = torch.cuda.Stream(dev, priority=0) if dev.type == "cuda" else None
         self._counter = torch.zeros(4, device=dev, dtype=torch.int32) if dev.type == "cuda" else None
+        # grid of the NVLS exchange kernel: two blocks per SM the gradient GEMMs leave free (it is bound by the bytes it
+        # keeps in flight; blocks that do not fit beside the GEMM would only start after it)
+        self.nvls_blocks = 32
+        if dev.type == "cuda" and self.gemm_sm_limit:
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            self.nvls_blocks = max(8, min(64, 2 * (sms - self.gemm_sm_limit)))
         if broadcast:
             # in place on the parameter itself (not on .data): the version counter moves, so a prototype staging that
             # was cached before wrapping is not reused with the broadcast values
@@ -170,7 +176,8 @@ class DataParallelSOM:
         if nv is not None and dw.data_ptr() == nv["dw"].data_ptr():
             from . import _lib
             _lib.check(_lib.lib().som_allreduce_mean_nvls(nv["mc"], nv["flag_ptrs"], nv["n"], dist.get_rank(self.group),
-                                                          self.world, _lib.stream_ptr(dw.device)), "som_allreduce_mean_nvls")
+                                                          self.world, self.nvls_blocks, _lib.stream_ptr(dw.device)),
+                       "som_allreduce_mean_nvls")
         else:
             all_reduce_mean(dw, self.group)
 
@@ -183,8 +190,9 @@ class DataParallelSOM:
         with torch.cuda.stream(self.comm_stream):
             sp = _lib.stream_ptr(dw.device)
             _lib.check(L.som_stream_wait_value(self._counter.data_ptr(), expected, sp), "som_stream_wait_value")
-            _lib.check(L.som_stream_write_value(self._counter.data_ptr(), 0, sp), "som_stream_write_value")
             self._reduce(dw)
+            # reset for the next backward (ordered before it through the join), off the exchange's critical path
+            _lib.check(L.som_stream_write_value(self._counter.data_ptr(), 0, sp), "som_stream_write_value")
         dw.record_stream(self.comm_stream)
         return lambda: cur.wait_stream(self.comm_stream)
 
@@ -243,7 +251,7 @@ class _ShardedLossFn(torch.autograd.Function):
                 # symmetric buffer; autograd gets a private copy because the buffer is reused by the next call
                 from . import _lib
                 _lib.check(_lib.lib().som_allreduce_nvls(nv["mc"], nv["flag_ptrs"], nv["n"], nv["rank"], nv["world"],
-                                                         1.0, _lib.stream_ptr(dx.device)), "som_allreduce_nvls")
+                                                         1.0, 64, _lib.stream_ptr(dx.device)), "som_allreduce_nvls")
                 grads = (dx.clone(),) + tuple(grads[1:])
             else:
                 all_reduce_sum(dx, ctx.group)
