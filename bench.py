@@ -317,6 +317,7 @@ def measure_som(env, name, wl, steps, warmup, sharded=False, with_e2e=False, wit
         from vit_som_b200.distributed import PrototypeShardedSOM
         torch.manual_seed(1234)                # identical full-map draw on every rank, each keeps its block
         layer = PrototypeShardedSOM(make_cfg(ms, D, fcn, T)).to(dev)
+        layer.async_dx = not args.sync_dx      # the dx exchange of a row chunk runs under the next chunk's kernels
         torch.manual_seed(4321)                # replicated latents
     else:
         torch.manual_seed(1234 + rank)
@@ -353,6 +354,8 @@ def measure_som(env, name, wl, steps, warmup, sharded=False, with_e2e=False, wit
             d, bmu = layer(x)
             loss = layer.som_loss(layer.compute_weights(bmu), d)
             loss.backward()
+            if sharded:
+                layer.wait_dx()
             return loss.detach()
         layer.grad_accumulator.zero_()
         losses = []
@@ -364,6 +367,8 @@ def measure_som(env, name, wl, steps, warmup, sharded=False, with_e2e=False, wit
             losses.append(loss.detach())
         if dp is not None:
             dp.reduce_accumulator()
+        if sharded:
+            layer.wait_dx()                    # join the asynchronous dx exchanges: the step ends with complete gradients
         return torch.stack(losses).sum()
 
     for _ in range(W_):
@@ -717,14 +722,19 @@ def measure_vit_som(env, tag, dataset, map_size, batch, steps, warmup):
         for n, p in model.vit.named_parameters():
             if n.startswith("dec_"):
                 p.requires_grad_(False)
-    dp = None
+    dp = bucket = None
     if world > 1:
-        from torch.nn.parallel import DistributedDataParallel as DDP
+        # data parallel: the prototype gradient is exchanged from inside the SOM backward (DataParallelSOM); the ViT
+        # and head gradients live in one flat bucket that is averaged with ONE all-reduce after backward (what DDP's
+        # bucketing amounts to for a 5 M parameter model, in a form a CUDA graph can capture)
         from vit_som_b200.distributed import DataParallelSOM
-        model.vit = DDP(model.vit, device_ids=[dev.index])
-        if model.classification:
-            model.cls_head = DDP(model.cls_head, device_ids=[dev.index])
+        from vit_som_b200.vit_som import FlatGradBucket
+        with torch.no_grad():
+            for p in list(model.vit.parameters()) + (list(model.cls_head.parameters()) if model.classification else []):
+                dist.broadcast(p, src=0)
         dp = DataParallelSOM(som, gemm_sm_limit=136, overlap=env.args.dp_overlap)
+        bucket = FlatGradBucket(list(model.vit.parameters()) +
+                                (list(model.cls_head.parameters()) if model.classification else []))
     opt_vit, opt_som = build_optimizers(model, capturable=True)
     size, chans = cfg["data"]["input_size"], cfg["data"]["num_channels"]
     img = torch.randn(batch, chans, size, size, device=dev)
@@ -732,9 +742,14 @@ def measure_vit_som(env, tag, dataset, map_size, batch, steps, warmup):
 
     def train_step():
         total, _ = model.training_loss(img, labels)
-        opt_vit.zero_grad(set_to_none=True)
+        if bucket is not None:
+            bucket.zero()
+        else:
+            opt_vit.zero_grad(set_to_none=True)
         opt_som.zero_grad(set_to_none=True)
         total.backward()
+        if bucket is not None:
+            bucket.all_reduce_mean()
         opt_vit.step()
         opt_som.step()
         return total
@@ -742,11 +757,10 @@ def measure_vit_som(env, tag, dataset, map_size, batch, steps, warmup):
     for _ in range(max(warmup, 3)):
         train_step()
     env.barrier()
-    # One GPU: the whole training step (ViT forward / backward, SOM kernels, both optimizers; ~700 launches) is captured
-    # in a CUDA graph - at these model sizes the eager step is bound by the host.  Data parallel: eager (DDP's bucket
-    # all-reduces and the side-stream exchange of DataParallelSOM are left to their own scheduling).
+    # The whole training step (ViT forward / backward, SOM kernels, gradient exchanges, both optimizers; ~700 launches)
+    # is captured in a CUDA graph - at these model sizes the eager step is bound by the host.
     graph = None
-    if world == 1 and not env.args.no_graph:
+    if not env.args.no_graph:
         try:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=env.compute_stream):
@@ -757,6 +771,8 @@ def measure_vit_som(env, tag, dataset, map_size, batch, steps, warmup):
             print(f"bench[vit {tag}]: CUDA graph capture failed ({exc!r}); eager step", file=sys.stderr)
             graph = None
             torch.cuda.synchronize(dev)
+    if env.max_over_ranks(0.0 if graph is not None else 1.0)[0] != 0.0:
+        graph = None                           # every rank takes the same path (the step contains collectives)
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     for _ in range(steps):
@@ -777,8 +793,8 @@ def measure_vit_som(env, tag, dataset, map_size, batch, steps, warmup):
            "step": "forward + CE/SOM loss (device-side gamma ramp, strided SOM input) + backward + AdamW (ViT) + fused "
                    "AdamW (prototypes); " + ("one CUDA graph per step" if graph is not None else "eager launches"),
            "parallelism": "single GPU" if world == 1 else
-                          f"dp{world}: torch DDP (ViT) + DataParallelSOM ({'NVLS' if dp.nvls is not None else 'NCCL'} "
-                          "prototype-gradient exchange inside the SOM backward)",
+                          f"dp{world}: one flat-bucket NCCL all-reduce (ViT + head gradients) + DataParallelSOM "
+                          f"({'NVLS' if dp.nvls is not None else 'NCCL'} prototype-gradient exchange inside the SOM backward)",
            "loss_finite": finite}
     if dp is not None:
         dp.detach()
@@ -803,6 +819,9 @@ def main():
                     help="data parallel: SMs the gradient GEMMs may occupy while the dW exchange runs (0 = all, -1 = 136)")
     ap.add_argument("--dp-overlap", default="counter", choices=["counter", "split", "after"],
                     help="data parallel: how the dW exchange overlaps the backward (see DataParallelSOM)")
+    ap.add_argument("--sync-dx", action="store_true",
+                    help="prototype-sharded: exchange the latent gradients inside backward (default: asynchronous, joined "
+                         "at the end of the step)")
     ap.add_argument("--no-extras", action="store_true", help="headline only: skip cfg5, ViT-SOM img/s and the parity check")
     ap.add_argument("--no-vit", action="store_true", help="skip the ViT-SOM img/s records")
     args = ap.parse_args()

@@ -242,17 +242,42 @@ class _ShardedLossFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_out):
+        nv = ctx.nvls
+        layer = getattr(ctx.state, "layer", None)
+        if nv is not None and nv.get("pending") is not None:
+            # the symmetric buffer still carries an exchange of an earlier call (asynchronous mode): the gradient GEMM
+            # of this call may only overwrite it once that exchange and its copy-out are done
+            torch.cuda.current_stream(nv["buf"].device).wait_event(nv["pending"])
+            nv["pending"] = None
         grads = ops.FusedLossFn.backward(ctx, g_out)
         dx = grads[0]
         if dx is not None:
-            nv = ctx.nvls
             if nv is not None and dx.data_ptr() == nv["buf"].data_ptr() and dx.dtype == torch.float32:
                 # partial dx of all shards summed in the NVSwitch (our two-shot multimem kernel), in place in the
-                # symmetric buffer; autograd gets a private copy because the buffer is reused by the next call
+                # symmetric buffer; autograd gets a private copy because the buffer is reused by a later call
                 from . import _lib
-                _lib.check(_lib.lib().som_allreduce_nvls(nv["mc"], nv["flag_ptrs"], nv["n"], nv["rank"], nv["world"],
-                                                         1.0, 64, _lib.stream_ptr(dx.device)), "som_allreduce_nvls")
-                grads = (dx.clone(),) + tuple(grads[1:])
+                L = _lib.lib()
+                if layer is not None and layer.async_dx:
+                    # asynchronous: exchange and copy-out run on the communication stream, under the next row chunk's
+                    # kernels; the caller joins with layer.wait_dx() before it reads the latent gradients
+                    cur = torch.cuda.current_stream(dx.device)
+                    comm = layer._comm_stream(dx.device)
+                    out = torch.empty_like(dx)
+                    comm.wait_stream(cur)
+                    with torch.cuda.stream(comm):
+                        _lib.check(L.som_allreduce_nvls(nv["mc"], nv["flag_ptrs"], nv["n"], nv["rank"], nv["world"], 1.0,
+                                                        layer.async_blocks, _lib.stream_ptr(dx.device)), "som_allreduce_nvls")
+                        out.copy_(dx)
+                    done = torch.cuda.Event()
+                    done.record(comm)
+                    out.record_stream(comm)
+                    nv["pending"] = done
+                    layer._dx_events.append(done)
+                    grads = (out,) + tuple(grads[1:])
+                else:
+                    _lib.check(L.som_allreduce_nvls(nv["mc"], nv["flag_ptrs"], nv["n"], nv["rank"], nv["world"], 1.0, 64,
+                                                    _lib.stream_ptr(dx.device)), "som_allreduce_nvls")
+                    grads = (dx.clone(),) + tuple(grads[1:])
             else:
                 all_reduce_sum(dx, ctx.group)
         return grads[:11]
@@ -278,8 +303,34 @@ class PrototypeShardedSOM(SOMLayer):
             raise ValueError(f"map of {self.k_total} cells cannot be sharded over {self.world} ranks")
         full = self.prototypes.data
         self.prototypes = torch.nn.Parameter(full[self.k_begin:self.k_end].clone())
-        self._nvls_dx = {}                    # (B, D) -> symmetric dx buffer + multicast mapping (None: NCCL)
+        self._nvls_dx = {}                    # (B, D, slot) -> symmetric dx buffer + multicast mapping (None: NCCL)
         self.use_nvls = os.environ.get("SOM_DP_NVLS", "1") != "0"
+        # Asynchronous exchange of the latent gradients (opt-in): backward returns as soon as the exchange of the partial
+        # dx is ENQUEUED on a communication stream, so it runs under the kernels of the next row chunk (two symmetric
+        # buffers alternate).  The returned gradient is complete only after wait_dx(): use it when the latents are
+        # leaves of the graph (row-chunked scoring of a large map); leave it off when dx flows on into an encoder.
+        self.async_dx = False
+        self.async_blocks = 32                # grid of the exchange kernel in asynchronous mode (two blocks per SM)
+        self._dx_events = []
+        self._dx_turn = 0
+        self._comm = None
+
+    def _comm_stream(self, dev):
+        if self._comm is None:
+            self._comm = torch.cuda.Stream(dev)
+        return self._comm
+
+    def wait_dx(self):
+        """Join the asynchronous dx exchanges enqueued so far: afterwards the current stream sees complete latent
+        gradients (no host synchronisation)."""
+        if self._dx_events:
+            cur = torch.cuda.current_stream(self.prototypes.device)
+            for ev in self._dx_events:
+                cur.wait_event(ev)
+            self._dx_events = []
+            for nv in self._nvls_dx.values():             # the current stream is now behind every exchange
+                if nv is not None:
+                    nv["pending"] = None
 
     # ---- checkpoints: the state dict holds the FULL map under the reference's key ---------------------------------
     def gather_prototypes(self) -> torch.Tensor:
@@ -312,10 +363,10 @@ class PrototypeShardedSOM(SOMLayer):
         super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
         self.invalidate_staging()
 
-    def _nvls_dx_buffer(self, B: int, D: int, dev):
+    def _nvls_dx_buffer(self, B: int, D: int, dev, slot: int = 0):
         """Symmetric [B, D] buffer for the partial dx of this rank plus what som_allreduce_nvls needs; allocated and
-        rendezvoused once per shape (a collective: every rank reaches it with the same shape at the same call)."""
-        key = (B, D)
+        rendezvoused once per shape and slot (a collective: every rank reaches it with the same shape at the same call)."""
+        key = (B, D, slot)
         if key in self._nvls_dx:
             return self._nvls_dx[key]
         state = None
@@ -332,7 +383,7 @@ class PrototypeShardedSOM(SOMLayer):
                     flags.zero_()
                     self._nvls_flags = (flags, symm_mem.rendezvous(flags, grp))
                 if int(getattr(hdl, "multicast_ptr", 0) or 0) != 0:
-                    state = {"buf": buf, "hdl": hdl, "n": B * D, "mc": int(hdl.multicast_ptr),
+                    state = {"buf": buf, "hdl": hdl, "n": B * D, "mc": int(hdl.multicast_ptr), "pending": None,
                              "flag_ptrs": int(self._nvls_flags[1].buffer_ptrs_dev), "rank": self.rank, "world": self.world}
             except Exception as exc:  # noqa: BLE001
                 self.nvls_error = repr(exc)
@@ -370,10 +421,15 @@ class PrototypeShardedSOM(SOMLayer):
         state.x_in, state.W_in = x, self.prototypes
         state.grad_accum = self.grad_accumulator
         state.nvls_dx = None
+        state.layer = self
+        slot = 0
+        if self.async_dx and torch.is_grad_enabled() and x.requires_grad:
+            slot = self._dx_turn                         # two buffers alternate under the asynchronous exchange
+            self._dx_turn ^= 1
         if torch.is_grad_enabled() and x.requires_grad and not torch.cuda.is_current_stream_capturing():
-            nv = self._nvls_dx_buffer(state.B, state.D, x.device)
+            nv = self._nvls_dx_buffer(state.B, state.D, x.device, slot)
         else:
-            nv = self._nvls_dx.get((state.B, state.D))   # capture / no_grad: only what already exists
+            nv = self._nvls_dx.get((state.B, state.D, slot))   # capture / no_grad: only what already exists
         if nv is not None:
             state.dx_out, state.nvls_dx = nv["buf"], nv
         dist_local = ops.DistanceFn.apply(x, self.prototypes, state)

@@ -117,7 +117,7 @@ def stage_rows(src: torch.Tensor, mode: int) -> Staging:
 class ForwardState:
     """What one forward leaves behind for the loss and the backward: raw and staged operands and the distances."""
     __slots__ = ("x", "W", "xs", "ws", "mode", "B", "K", "D", "dist_buf", "ldd", "packed", "idx_offset",
-                 "x_in", "W_in", "grad_accum", "dw_out", "dx_out", "nvls_dx")
+                 "x_in", "W_in", "grad_accum", "dw_out", "dx_out", "nvls_dx", "layer")
 
 
 def forward(x: torch.Tensor, W: torch.Tensor, mode: int, ws: Staging | None = None, stage_w: bool = True,
@@ -176,6 +176,7 @@ def forward(x: torch.Tensor, W: torch.Tensor, mode: int, ws: Staging | None = No
     st.dw_out = None             # optional caller-owned [K, D] destination of dW (data parallel: a symmetric buffer)
     st.dx_out = None             # optional caller-owned [B, D] destination of dx (prototype shards: a symmetric buffer)
     st.nvls_dx = None
+    st.layer = None
     return st, bmu
 
 

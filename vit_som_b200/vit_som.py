@@ -180,6 +180,32 @@ def build_optimizers(model: ViTSOM, fused_prototypes: bool = True, capturable: b
             FusedPrototypeAdamW(model.som_layer, lr=lr, betas=betas))
 
 
+class FlatGradBucket:
+    """Gradients of a parameter list as views of ONE flat buffer, averaged over the ranks with one all-reduce.
+
+    What DDP's bucketing does for the (small) ViT of ViT-SOM, reduced to a form that can be captured in a CUDA graph
+    together with the rest of the training step: ``zero()`` before backward, ``all_reduce_mean()`` after it."""
+
+    def __init__(self, params, group=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = group
+        n = sum(p.numel() for p in self.params)
+        first = self.params[0]
+        self.flat = torch.zeros(n, device=first.device, dtype=first.dtype)
+        o = 0
+        for p in self.params:
+            p.grad = self.flat[o:o + p.numel()].view_as(p)
+            o += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+
+    def all_reduce_mean(self):
+        import torch.distributed as dist
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+
+
 def reference_yaml_config(dataset: str, map_size, batch_size: int):
     """The shipped ViT-SOM YAML of ``dataset`` as a dict (only the keys the model reads), with the map size and batch
     size BASELINE.json names.  cifar-10: configs/vit_som/vit_som_cifar-10.yaml; tiny-imagenet: ..._tiny-imagenet.yaml."""
