@@ -302,7 +302,8 @@ void som_set_tuning(int bn_override, int kchunk);
 void som_set_cta_group(int cg);
 /* Diagnostics: bit 0 = no TMA loads after the first ring pass, bit 1 = no tensor-core instructions, bit 2 / 3 = gradient
  * epilogue without src loads / without stores (results are garbage with any of these); bit 4 = one 2-D TMA operation per
- * MN-major panel instead of one 3-D operation per tile (results unchanged). */
+ * MN-major panel instead of one 3-D operation per tile (results unchanged); bit 5 = always the generic fused loss kernel
+ * instead of the straight-line fast path for aligned square maps (results equal to rounding). */
 void som_set_debug(int bits);
 /* Diagnostics: device buffer of 16 uint64 in which CTA 0 of the pair kernel stamps %globaltimer (ns) at its phase
  * boundaries (start, setup done, producer done, issuer done, last accumulators ready, epilogue done, pair synced,

@@ -227,6 +227,42 @@ def test_programmatic_dependent_launch_does_not_change_results(cuda_device):
         assert (a == b) if isinstance(a, float) else torch.equal(a, b)
 
 
+@pytest.mark.parametrize("fcn", ["euclidean", "cosine"])
+@pytest.mark.parametrize("shape", [(1024, (40, 40), 512), (300, (24, 20), 96), (4096, (64, 64), 64), (37, (8, 12), 40)])
+def test_fast_loss_kernel_matches_generic(shape, fcn, cuda_device):
+    """The straight-line loss kernel for aligned square maps against the generic one (som_set_debug bit 5 forces it):
+    same BMUs and distances, loss and gradients equal to rounding; both deterministic."""
+    from vit_som_b200 import _lib
+    B, ms, D = shape
+    torch.manual_seed(15)
+    layer = make_layer(ms, D, fcn, 2.5)
+    x = torch.randn(B, D, device="cuda", requires_grad=True)
+    L = _lib.lib()
+    out = {}
+    for bits in (0, 32, 0):
+        L.som_set_debug(bits)
+        try:
+            d, bmu, loss = step(layer, x, 0.9)
+            torch.cuda.synchronize()
+        finally:
+            L.som_set_debug(0)
+        cur = (d.detach().clone(), bmu.clone(), loss.item(), x.grad.clone(), layer.prototypes.grad.clone())
+        if bits in out:
+            for a, b in zip(cur, out[bits]):                       # the fast path repeats bit for bit
+                assert (a == b) if isinstance(a, float) else torch.equal(a, b)
+        out[bits] = cur
+    fast, gen = out[0], out[32]
+    assert torch.equal(fast[0], gen[0]) and torch.equal(fast[1], gen[1])
+    assert abs(fast[2] - gen[2]) <= 2e-6 * abs(gen[2])
+    assert O.rel_err(fast[3].cpu().numpy(), gen[3].cpu().numpy()) < 2e-6
+    assert O.rel_err(fast[4].cpu().numpy(), gen[4].cpu().numpy()) < 2e-6
+    r64 = O.step(x.detach().cpu().numpy(), layer.prototypes.detach().cpu().numpy(), O.grid_positions(ms), 2.5, fcn, 0.9,
+                 np.float64, bmu_override=fast[1].cpu().numpy())
+    assert abs(fast[2] - float(r64.loss)) <= LOSS_TOL * abs(float(r64.loss))
+    assert O.rel_err(fast[3].cpu().numpy(), r64.grad_x) < GRAD_TOL
+    assert O.rel_err(fast[4].cpu().numpy(), r64.grad_w) < GRAD_TOL
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # fused prototype AdamW
 # ------------------------------------------------------------------------------------------------------------------

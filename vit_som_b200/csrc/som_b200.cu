@@ -31,6 +31,7 @@ std::atomic<int> g_debug{0};            // GemmShape::debug (diagnostic runs of 
 std::atomic<int> g_cg_override{0};
 std::atomic<unsigned long long*> g_dbg_times{nullptr};
 std::atomic<int> g_streamk{0};          // -1 = never, 0 = cost model, 1 = whenever possible
+std::atomic<int> g_loss_fast{1};        // 0 = always the generic loss kernel (diagnostics / tests)
 std::atomic<int> g_pdl{1};              // 1 = launch with programmatic stream serialization (kernel prologues overlap the predecessor's tail)
 
 int fail(int code, const std::string& msg) {
@@ -170,14 +171,20 @@ int64_t streamk_workers(int64_t units, int64_t slots, int bn, int64_t ws_floats,
   workers = std::min<int64_t>(workers, SK_FLAG_WORDS / (16 * phases));
   return workers >= 2 ? workers : 0;
 }
+constexpr double HANDOVER_NS = 1300.0;      // one partial tile added by a tile's owner outside its epilogue loop
 double streamk_cost_ns(int64_t units, int64_t workers, int64_t nkb_typ, int bn, bool mn_major) {
   const int64_t per_worker = (units + workers - 1) / workers;
   const double t_epi = 1500.0 + 80.0 * (static_cast<double>(bn) / 2);
   // the pair kernel always has two TMEM buffers: only the last drain of a worker is exposed, the others cost a
   // stall of the issuer when they outlast an accumulation chunk (charged at a quarter)
   const double segs = std::max(1.0, static_cast<double>(per_worker) / static_cast<double>(nkb_typ)) + 1.0;
+  // a tile that is cut into many pieces: its owner adds the other pieces' partial tiles one after the other (measured
+  // ~1.3 us each: flag, fetch, add; the first one is folded into the epilogue loop) - config 3's forward, one tile with
+  // 384 k-blocks spread over 74 pairs, spent 95 of its 108 us there
+  const double pieces = static_cast<double>(nkb_typ) / static_cast<double>(std::max<int64_t>(per_worker, 1));
+  const double handover = HANDOVER_NS * std::max(0.0, pieces - 2.0);
   return static_cast<double>(per_worker) * per_kb_ns(2, bn, static_cast<double>(workers) * 2, mn_major) +
-         t_epi + (segs - 1.0) * t_epi * 0.25 + 4000.0 + 2000.0;
+         t_epi + (segs - 1.0) * t_epi * 0.25 + 4000.0 + 2000.0 + handover;
 }
 
 TileChoice pick_tile(int64_t M, int64_t N, int64_t Kred, int sms, int b_mn, int64_t ws_floats, int bn_req) {
@@ -217,7 +224,7 @@ TileChoice pick_tile(int64_t M, int64_t N, int64_t Kred, int sms, int b_mn, int6
       }
       // tile-aligned split-K: fewer tiles than pairs -> every tile cut into `split` equal pieces, one partial-tile
       // hand-over per piece and no slivers (preferred over even ranges at equal cost: it exchanges less)
-      // The owner adds the other pieces' partial tiles one after the other (~0.7 us each: flag, fetch, add), so a long
+      // The owner adds the other pieces' partial tiles one after the other (~1.3 us each: flag, fetch, add), so a long
       // reduction over few tiles (config 3: one 128 x 16 tile with 384 k-blocks) wants fewer, longer pieces than the
       // pairs would allow: the split is the one that minimises  piece time + (split - 1) hand-overs.
       const int64_t split_max = tiles > 0 ? std::min<int64_t>(slots / tiles, nkb / 8) : 0;
@@ -226,7 +233,7 @@ TileChoice pick_tile(int64_t M, int64_t N, int64_t Kred, int sms, int b_mn, int6
       for (int64_t sp = 2; sp <= split_max && tiles * sp <= workers; ++sp) {
         const int64_t piece = (nkb + sp - 1) / sp;
         const double c = static_cast<double>(piece) * per_kb_ns(2, bn, static_cast<double>(tiles * sp) * 2, panel_loads) +
-                         t_epi + 4000.0 + 2000.0 + 700.0 * static_cast<double>(sp - 2);
+                         t_epi + 4000.0 + 2000.0 + HANDOVER_NS * static_cast<double>(sp - 2);
         if (c < split_cost) { split_cost = c; split = sp; }
       }
       if (split >= 2) {
@@ -458,6 +465,19 @@ __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return __uint_as_float(u);
+}
+// The same rounding (nearest, ties away from zero) for values that are finite or inf: on sm_100a cvt.rna.tf32.f32 is
+// emulated by four instructions (an |x| < inf test, add, select, mask - cuobjdump); adding half an ulp to the magnitude
+// bits and clearing the 13 low bits is the same function on all finite values and inf, in two.  NOT for NaN inputs (the
+// canonical NaN 0x7fffffff would wrap to -0): used by the fused loss kernel only, where a NaN operand means a NaN
+// distance and therefore a NaN loss that the caller sees.
+__device__ __forceinline__ float tf32_rna_finite(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -977,6 +997,175 @@ loss_coeffs_kernel(const float* __restrict__ dist, long long ldd, const long lon
   }
 }
 
+// Fast path of the fused loss kernel for what the training step of a square map always presents: 16-byte aligned
+// rows, K and the grid's column count multiples of 4 (a lane's 4 columns then lie in ONE grid row), backward staging
+// requested.  Same block / warp / lane decomposition and the same outputs as loss_coeffs_kernel<true>, but straight-line
+// code: the generic kernel spends ~70 instructions per element (ncu: 2.7 warp instructions per cycle and SM, issue
+// bound at 3.9 TB/s on a 4096 x 16384 chunk) on per-element predicates, 64-bit index arithmetic and two table lookups
+// per element; here the row factor of the weight is looked up once per lane and row, inv_count is folded into it,
+// pointers advance by increments and nothing is predicated per element.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+loss_coeffs_fast_kernel(const float* __restrict__ dist, long long ldd, const long long* __restrict__ bmu,
+                        int grid_rows, int grid_cols, long long B, long long K, long long k_offset,
+                        const float* __restrict__ T_dev, float inv_count,
+                        float* __restrict__ r_hi, float* __restrict__ r_lo, long long ldr,
+                        float* __restrict__ row_part, int n_row_parts, float* __restrict__ col_part,
+                        float* __restrict__ partials, float* __restrict__ loss_out, int rows_per_block) {
+  som::pdl_wait();
+  som::pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rh = warp >> 2, cs = warp & 3;
+  const int half_rows = rows_per_block >> 1;
+  const long long k0 = static_cast<long long>(blockIdx.y) * LC_COLS + cs * 128 + lane * 4;
+  const long long b_base = static_cast<long long>(blockIdx.x) * rows_per_block + rh * half_rows;
+  const int slab = static_cast<int>(blockIdx.y) * 4 + cs;
+  const bool col_ok = k0 < K;                              // K % 4 == 0: all four columns of the lane or none
+  __shared__ float lred[8];
+  __shared__ float csum[LC_COLS];
+  __shared__ float tab[LC_MAX_TAB];
+  __shared__ float tab_s[LC_MAX_TAB];                      // inv_count * tab: the row factor carries the 1 / (B K)
+
+  const float T = __ldg(T_dev);
+  const float two_t2 = 2.f * (T * T);
+  const unsigned kg = static_cast<unsigned>(k_offset + k0);
+  const int rk = static_cast<int>(kg / static_cast<unsigned>(grid_cols));
+  const int ck = static_cast<int>(kg - static_cast<unsigned>(rk) * static_cast<unsigned>(grid_cols));
+  {
+    const int ntab = max(grid_rows, grid_cols);
+    for (int d = threadIdx.x; d < ntab; d += blockDim.x) {
+      const float fd = static_cast<float>(d);
+      const float e = expf(-(fd * fd) / two_t2);
+      tab[d] = e;
+      tab_s[d] = inv_count * e;
+    }
+    __syncthreads();
+  }
+  const long long rows_left = B - b_base;                  // rows of this warp that exist (may be <= 0)
+  const int nrows = rows_left <= 0 ? 0 : (rows_left < half_rows ? static_cast<int>(rows_left) : half_rows);
+  const float* dp = dist + b_base * ldd + k0;
+  float* hp = r_hi + b_base * ldr + k0;
+  float* lp = r_lo + b_base * ldr + k0;
+  float* rp = row_part + b_base * n_row_parts + slab;
+  const bool slab_ok = slab < n_row_parts;
+  auto load4 = [&](int r, float4& v) {
+    v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col_ok && r < nrows) v = __ldg(reinterpret_cast<const float4*>(dp + static_cast<long long>(r) * ldd));   // r: row of the warp
+  };
+  float colsum0 = 0.f, colsum1 = 0.f, colsum2 = 0.f, colsum3 = 0.f, lsum = 0.f;
+  // One group = 4 rows.  All arithmetic runs unconditionally (missing rows / columns contribute exact zeros: their
+  // distances load as 0 and their row factor is 0), only the stores are predicated.
+  auto process = [&](const float4 (&dg)[4], int r4) {
+    // BMU cell of these 4 rows: lane r loads row r, one shuffle per row broadcasts (row << 16 | column)
+    int cell = 0;
+    if (lane < 4 && r4 + lane < nrows) {
+      const unsigned ub = static_cast<unsigned>(bmu[b_base + r4 + lane]);
+      const unsigned rb = ub / static_cast<unsigned>(grid_cols);
+      cell = static_cast<int>((rb << 16) | (ub - rb * static_cast<unsigned>(grid_cols)));
+    }
+    float t[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int rc = __shfl_sync(0xffffffffu, cell, r);
+      const bool row_ok = r4 + r < nrows;                  // warp-uniform
+      const int rb = rc >> 16, cb = rc & 0xffff;
+      const float er = row_ok ? tab_s[abs(rk - rb)] : 0.f;  // inv_count * exp(-dr^2 / 2T^2)
+      const int dc0 = ck - cb;
+      const float w0 = er * tab[abs(dc0)], w1 = er * tab[abs(dc0 + 1)], w2 = er * tab[abs(dc0 + 2)], w3 = er * tab[abs(dc0 + 3)];
+      const float4 d = dg[r];
+      lsum = fmaf(w0, d.x, lsum); lsum = fmaf(w1, d.y, lsum); lsum = fmaf(w2, d.z, lsum); lsum = fmaf(w3, d.w, lsum);
+      float4 rv, term;
+      if (MODE == 0) {
+        // ATen: ratio = grad / dist, masked_fill_(dist == 0, 0).  w * rcp(d): 2 ulp; rcp(0) = inf is selected away
+        rv.x = d.x == 0.f ? 0.f : w0 * fast_rcp(d.x);
+        rv.y = d.y == 0.f ? 0.f : w1 * fast_rcp(d.y);
+        rv.z = d.z == 0.f ? 0.f : w2 * fast_rcp(d.z);
+        rv.w = d.w == 0.f ? 0.f : w3 * fast_rcp(d.w);
+        term = rv;
+      } else {
+        rv = make_float4(w0, w1, w2, w3);
+        term = make_float4(w0 * (1.f - d.x), w1 * (1.f - d.y), w2 * (1.f - d.z), w3 * (1.f - d.w));
+      }
+      float4 h, l;
+      h.x = tf32_rna_finite(rv.x); h.y = tf32_rna_finite(rv.y); h.z = tf32_rna_finite(rv.z); h.w = tf32_rna_finite(rv.w);
+      l.x = tf32_rna_finite(rv.x - h.x); l.y = tf32_rna_finite(rv.y - h.y);
+      l.z = tf32_rna_finite(rv.z - h.z); l.w = tf32_rna_finite(rv.w - h.w);
+      if (col_ok && row_ok) {
+        *reinterpret_cast<float4*>(hp) = h;
+        *reinterpret_cast<float4*>(lp) = l;
+      }
+      colsum0 += term.x; colsum1 += term.y; colsum2 += term.z; colsum3 += term.w;
+      t[r] = col_ok ? (term.x + term.y) + (term.z + term.w) : 0.f;
+      hp += ldr; lp += ldr;
+    }
+    // the four row sums of the group in one transposed butterfly (6 shuffles instead of 20; a fixed pattern, so the
+    // result is the same in every run): after the 16- and 8-steps a lane carries ONE of the rows, selected by its bits
+    // 4 and 3; lanes 0, 16, 8, 24 end up with the totals of rows 0, 1, 2, 3
+    const bool b16 = (lane & 16) != 0, b8 = (lane & 8) != 0;
+    const float v01 = (b16 ? t[1] : t[0]) + __shfl_xor_sync(0xffffffffu, b16 ? t[0] : t[1], 16);
+    const float v23 = (b16 ? t[3] : t[2]) + __shfl_xor_sync(0xffffffffu, b16 ? t[2] : t[3], 16);
+    float u = (b8 ? v23 : v01) + __shfl_xor_sync(0xffffffffu, b8 ? v01 : v23, 8);
+    u += __shfl_xor_sync(0xffffffffu, u, 4);
+    u += __shfl_xor_sync(0xffffffffu, u, 2);
+    u += __shfl_xor_sync(0xffffffffu, u, 1);
+    const int row = (b16 ? 1 : 0) + (b8 ? 2 : 0);
+    if ((lane & 7) == 0 && slab_ok && r4 + row < nrows) rp[static_cast<long long>(row) * n_row_parts] = u;
+    rp += 4 * n_row_parts;
+  };
+  // two register sets of distances alternate (no copies): while one group is processed the next one is in flight
+  float4 da[4], db[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) load4(r, da[r]);
+  for (int r4 = 0; r4 < nrows; r4 += 8) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) load4(r4 + 4 + r, db[r]);
+    process(da, r4);
+    if (r4 + 4 >= nrows) break;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) load4(r4 + 8 + r, da[r]);
+    process(db, r4 + 4);
+  }
+  if (!col_ok) { colsum0 = colsum1 = colsum2 = colsum3 = 0.f; lsum = 0.f; }
+  lsum = warp_sum(lsum);
+  if (lane == 0) lred[warp] = lsum;
+  if (rh == 1) {
+    float* c = csum + cs * 128 + lane * 4;
+    c[0] = colsum0; c[1] = colsum1; c[2] = colsum2; c[3] = colsum3;
+  }
+  __syncthreads();
+  if (rh == 0 && col_ok) {
+    const float* c = csum + cs * 128 + lane * 4;
+    *reinterpret_cast<float4*>(col_part + static_cast<long long>(blockIdx.x) * K + k0) =
+        make_float4(colsum0 + c[0], colsum1 + c[1], colsum2 + c[2], colsum3 + c[3]);
+  }
+  if (warp != 0) return;
+  // deterministic loss: per-block partial (already scaled by inv_count), the last block's first warp adds all partials
+  // in a fixed order in fp64
+  const long long nblocks = static_cast<long long>(gridDim.x) * gridDim.y;
+  unsigned int* counter = reinterpret_cast<unsigned int*>(partials);
+  partials += 2;
+  unsigned int done = 0;
+  if (lane == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += lred[i];
+    partials[static_cast<long long>(blockIdx.y) * gridDim.x + blockIdx.x] = t;
+    __threadfence();
+    done = atomicAdd(counter, 1u);
+  }
+  done = __shfl_sync(0xffffffffu, done, 0);
+  if (done != nblocks - 1) return;
+  __threadfence();
+  double acc = 0.0;
+  for (long long i = lane; i < nblocks; i += 32) acc += static_cast<double>(__ldcg(partials + i));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    *loss_out = static_cast<float>(acc);
+    *counter = 0u;
+  }
+}
+
 // Rows per block of the fused loss kernel: as many as keep ~8 blocks per SM in flight (fewer, taller blocks amortise
 // the per-block setup and shorten the column-sum tables), between LC_ROWS and 128.
 inline int loss_rows_per_block(int64_t B, int64_t K, int sms) {
@@ -1263,7 +1452,11 @@ void som_set_tuning(int bn_override, int kchunk) {
   g_bn_override.store(bn_override);
   if (kchunk > 0) g_kchunk.store(kchunk);
 }
-void som_set_debug(int bits) { g_debug.store(bits & ~16); g_tma3d.store((bits & 16) ? 0 : 1); }
+void som_set_debug(int bits) {
+  g_debug.store(bits & ~(16 | 32));
+  g_tma3d.store((bits & 16) ? 0 : 1);
+  g_loss_fast.store((bits & 32) ? 0 : 1);
+}
 void som_set_debug_times(unsigned long long* dev_buf) { g_dbg_times.store(dev_buf); }
 void som_set_pdl(int on) { g_pdl.store(on ? 1 : 0); }
 void som_set_streamk(int mode) { g_streamk.store(mode < 0 ? -1 : (mode > 0 ? 1 : 0)); }
@@ -1465,7 +1658,23 @@ int som_loss_fused(const float* dist, int64_t ldd, const int64_t* bmu, const flo
   const int n_row_parts = static_cast<int>((K + 127) / 128);
   dim3 grid(static_cast<unsigned>((B + rpb - 1) / rpb), static_cast<unsigned>((K + LC_COLS - 1) / LC_COLS));
   const long long* bmu_ll = reinterpret_cast<const long long*>(bmu);
-  if (square)
+  // straight-line fast path: square grid, backward staging, everything 16-byte aligned, 4 | K, 4 | grid columns, 4 | k_offset
+  const bool fast = square && r_hi && g_loss_fast.load() && (K & 3) == 0 && (grid_cols & 3) == 0 && (k_offset & 3) == 0 &&
+                    (ldd & 3) == 0 && (ldr & 3) == 0 && grid_rows < 65536 && grid_cols < 65536 &&
+                    ((reinterpret_cast<uintptr_t>(dist) | reinterpret_cast<uintptr_t>(r_hi) | reinterpret_cast<uintptr_t>(r_lo) |
+                      reinterpret_cast<uintptr_t>(col_part)) & 15) == 0;
+  if (fast) {
+    if (mode == SOM_MODE_EUCLIDEAN)
+      SOM_CUDA(launch_kernel(loss_coeffs_fast_kernel<0>, grid, dim3(256), 0, as_stream(stream), dist, static_cast<long long>(ldd),
+                             bmu_ll, grid_rows, grid_cols, static_cast<long long>(B), static_cast<long long>(K),
+                             static_cast<long long>(k_offset), T_dev, inv_count, r_hi, r_lo, static_cast<long long>(ldr),
+                             row_part, n_row_parts, col_part, scratch, loss_out, rpb));
+    else
+      SOM_CUDA(launch_kernel(loss_coeffs_fast_kernel<1>, grid, dim3(256), 0, as_stream(stream), dist, static_cast<long long>(ldd),
+                             bmu_ll, grid_rows, grid_cols, static_cast<long long>(B), static_cast<long long>(K),
+                             static_cast<long long>(k_offset), T_dev, inv_count, r_hi, r_lo, static_cast<long long>(ldr),
+                             row_part, n_row_parts, col_part, scratch, loss_out, rpb));
+  } else if (square)
     SOM_CUDA(launch_kernel(loss_coeffs_kernel<true>, grid, dim3(256), 0, as_stream(stream), dist, static_cast<long long>(ldd),
                            bmu_ll, grid_pos, grid_rows, grid_cols, static_cast<long long>(B), static_cast<long long>(K),
                            static_cast<long long>(k_offset), T_dev, inv_count, mode, r_hi, r_lo, static_cast<long long>(ldr),
