@@ -817,7 +817,7 @@ def main():
                     help="rows per module call (0 = 4096, times the world size when prototypes are sharded)")
     ap.add_argument("--gemm-sms", type=int, default=-1,
                     help="data parallel: SMs the gradient GEMMs may occupy while the dW exchange runs (0 = all, -1 = 136)")
-    ap.add_argument("--dp-overlap", default="counter", choices=["counter", "split", "after"],
+    ap.add_argument("--dp-overlap", default="split", choices=["counter", "split", "after"],
                     help="data parallel: how the dW exchange overlaps the backward (see DataParallelSOM)")
     ap.add_argument("--sync-dx", action="store_true",
                     help="prototype-sharded: exchange the latent gradients inside backward (default: asynchronous, joined "

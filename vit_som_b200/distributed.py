@@ -83,15 +83,25 @@ class DataParallelSOM:
     """Attach DDP-equivalent gradient averaging to a :class:`SOMLayer` whose batch is sharded over ranks.
 
     ``DataParallelSOM(layer)`` broadcasts the prototypes from rank 0 and installs itself as the layer's dW hook.  The
-    backward stays ONE launch for both gradient GEMMs (dW tiles first); the exchange of dW (+ 1/world scaling) is
-    enqueued on a communication stream behind a stream-ordered wait on the counter that the dW epilogues raise
-    (``som_stream_wait_value``: executed by the GPU front end, no SM is held while waiting), so it runs under the dx
-    tiles of the same launch - and, in a full model, under the ViT backward.  The GEMM launch leaves a few SMs to the
-    exchange kernel (``gemm_sm_limit``, a per-call argument of the C-ABI).  The compute stream joins the communication
-    stream before backward returns dW to autograd.  The local loss is the mean over the local rows, as under DDP."""
+    exchange of dW (+ 1/world scaling) runs on a communication stream beside the rest of the backward - and, in a full
+    model, under the ViT backward; the compute stream joins before backward returns dW to autograd.  The local loss is
+    the mean over the local rows, as under DDP.  ``overlap`` selects how the exchange is started:
+
+    * ``"split"`` (default; fastest in the measurements of round 2): the dW GEMM is a launch of its own, the exchange
+      starts when it is done and runs beside the dx GEMM, which leaves ``148 - gemm_sm_limit`` SMs to it;
+    * ``"counter"``: the backward stays ONE launch for both gradient GEMMs with a two-phase stream-K schedule (every CTA
+      pair works off its share of the dW tiles first); the dW epilogues raise a counter and the exchange sits behind a
+      stream-ordered wait on it (``som_stream_wait_value``: executed by the GPU front end, no SM is held while waiting),
+      so it runs under the dx half of the same launch;
+    * ``"after"``: one fused launch, exchange after it (no overlap; the baseline of the other two).
+
+    Measured, config 2 (dW = 20 MB), ms per step at 1 / 2 / 8 GPUs: split 0.197 / 0.240 / 0.239, counter 0.197 / 0.248 /
+    0.245, after - / 0.289 / -.  The exchange itself takes 75-80 us at any GPU count (two-shot NVLS all-reduce at the
+    NVSwitch's rate, 274 GB/s algorithm bandwidth) and cannot start before dW is complete (~65-75 us into the backward),
+    which bounds the step of this layer-only benchmark at ~0.23 ms; in ViT-SOM training it hides under the ViT backward."""
 
     def __init__(self, layer: SOMLayer, group=None, broadcast: bool = True, gemm_sm_limit: int | None = None,
-                 nvls: bool | None = None, overlap: str = "counter"):
+                 nvls: bool | None = None, overlap: str = "split"):
         if not dist.is_initialized():
             raise SomError("DataParallelSOM needs an initialised torch.distributed process group")
         if overlap not in ("counter", "split", "after"):
