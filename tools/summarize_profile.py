@@ -4,8 +4,8 @@
 
 Inputs : gpurun_out/launches_<tag>.csv   (ncu --metrics gpu__time_duration.sum launch list)
          gpurun_out/prof_<tag>.ncu-rep   (ncu --set full capture of the hot kernels)
-Outputs: profiles/<tag>_launches.txt, profiles/<tag>_ncu_kernels.txt, profiles/traffic_r01.json (per-launch DRAM
-         bytes of the tensor-core GEMM, read by bench.py for roofline.traffic)
+Outputs: profiles/<tag>_launches.txt, profiles/<tag>_ncu_kernels.txt, profiles/traffic_r02.json (per-launch DRAM
+         bytes of the tensor-core GEMM, keyed "<workload>@n<GPUs>", read by bench.py for roofline.traffic)
 """
 import csv
 import json
@@ -27,6 +27,7 @@ METRICS = [
     ("launch__registers_per_thread", "registers/thread"),
     ("launch__shared_mem_per_block_dynamic", "dynamic smem/block"),
     ("smsp__inst_executed.sum", "warp instructions"),
+    ("sm__inst_executed.avg.per_cycle_active", "warp instr / cycle / SM"),
 ]
 
 
@@ -46,7 +47,8 @@ def launches(tag, out):
     step = None
     for a, b in zip(starts, starts[1:]):
         seg = recs[a:b]
-        if sum("gemm3x" in r[0] for r in seg) in (2, 3) and sum("prep_rows" in r[0] for r in seg) == 1:
+        if sum("gemm3x" in r[0] for r in seg) in (2, 3) and sum("prep_rows" in r[0] for r in seg) == 1 and \
+                sum("loss_coeffs" in r[0] for r in seg) == 1:
             step = seg
     with open(out, "w") as f:
         f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none; python bench.py --steps 2 --warmup 3 "
@@ -90,14 +92,14 @@ def kernels(tag, out, workload):
                 tr = sum(float(d[idx[m]]) * conv[units[idx[m]]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
                 gemm_traffic.setdefault(name, []).append(tr)
     if gemm_traffic:
-        tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
+        tpath = os.path.join(ROOT, "profiles", "traffic_r02.json")
         cur = {}
         if os.path.exists(tpath):
             with open(tpath) as f:
                 cur = json.load(f)
         # one step = one launch of each GEMM kernel (forward, fused backward): average over the kinds
         per_kind = {k: sum(v) / len(v) for k, v in gemm_traffic.items()}
-        cur[workload] = {"dram_bytes_per_launch": sum(per_kind.values()) / len(per_kind),
+        cur[f"{workload}@n1"] = {"dram_bytes_per_launch": sum(per_kind.values()) / len(per_kind),
                          "per_kernel": per_kind, "note": "ncu --set full, cold L2 (flushed before every replay pass)",
                          "source": f"profiles/{tag}_ncu_kernels.txt"}
         with open(tpath, "w") as f:
