@@ -359,8 +359,12 @@ def measure_som(env, name, wl, steps, warmup, sharded=False, with_e2e=False, wit
             return loss.detach()
         layer.grad_accumulator.zero_()
         losses = []
-        for x in xs:
+        for i, x in enumerate(xs):
             x.grad = None
+            if sharded and layer.async_dx:
+                # the last row chunk has no successor to hide its dx exchange under: its backward computes the dx tiles
+                # first and the exchange runs beside the dW tiles of the same launch
+                layer.dx_overlap = "kernel" if i == len(xs) - 1 and not args.no_kernel_overlap else "stream"
             d, bmu = layer(x)
             loss = layer.som_loss(layer.compute_weights(bmu), d)
             loss.backward()
@@ -822,6 +826,8 @@ def main():
     ap.add_argument("--sync-dx", action="store_true",
                     help="prototype-sharded: exchange the latent gradients inside backward (default: asynchronous, joined "
                          "at the end of the step)")
+    ap.add_argument("--no-kernel-overlap", action="store_true",
+                    help="prototype-sharded: do not overlap the last chunk's dx exchange inside its backward launch")
     ap.add_argument("--no-extras", action="store_true", help="headline only: skip cfg5, ViT-SOM img/s and the parity check")
     ap.add_argument("--no-vit", action="store_true", help="skip the ViT-SOM img/s records")
     args = ap.parse_args()

@@ -224,10 +224,13 @@ int som_backward_dx(const float* r_hi, const float* r_lo, int64_t ldr,
  * Both gradient GEMMs above in ONE persistent CTA-pair launch (their tiles share one stream-K work list, dW tiles
  * first): same results as som_backward_dw followed by som_backward_dx, one prologue / tail instead of two.  Needs the
  * GEMM workspace; without it (or for tiny shapes) it issues the two launches.
- * Data parallel: dw_done != NULL -> every finished 32-row slab of dW adds 1 to *dw_done (a zero-initialised device
- * word) and *dw_done_expected (host) receives the final count, so the exchange of dW can start from another stream
- * behind som_stream_wait_value(dw_done, expected) while the dx tiles are still running; -1 = not counted (fallback
- * launches: order the exchange after this call).
+ * Counted launches (done != NULL): a two-phase schedule - every CTA pair first works off its share of the COUNTED
+ * GEMM's tiles (dW when count_dx == 0: data parallelism; dx when count_dx != 0: prototype shards), then its share of
+ * the other's.  Every finished 32-row slab of the counted result adds 1 to *done (a zero-initialised device word) and
+ * *done_expected (host) receives the final count, so the exchange of that result can start from another stream behind
+ * som_stream_wait_value(done, expected) while the other GEMM's tiles are still running; sm_limit > 0 then bounds the
+ * SMs of the SECOND phase only (the pairs beyond it exit after phase 1 and free their SMs for the exchange kernel).
+ * *done_expected = -1: not counted (fallback launches: order the exchange after this call).
  */
 int som_backward_fused(const float* r_hi, const float* r_lo, int64_t ldr,
                        const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo, int64_t ld_stage,
@@ -236,7 +239,7 @@ int som_backward_fused(const float* r_hi, const float* r_lo, int64_t ldr,
                        const float* x_aux, const float* w_aux,
                        const float* g_dev, int64_t B, int64_t K, int64_t D, int mode,
                        float* dW, int64_t lddw, int accumulate_dw, float* dx, int64_t lddx,
-                       int sm_limit, unsigned int* dw_done, int64_t* dw_done_expected,
+                       int sm_limit, int count_dx, unsigned int* done, int64_t* done_expected,
                        float* ws, int64_t ws_floats, void* stream);
 
 /* Stream-ordered memory operations (cuStreamWaitValue32 GEQ / cuStreamWriteValue32): `stream` proceeds once

@@ -55,40 +55,53 @@ def spawn(fn, *args, world=2):
             pytest.fail("multi-GPU worker timed out")
 
 
-def _sharded_worker(rank, world, fcn):
+def _sharded_worker(rank, world, fcn, dx_mode="sync"):
     from vit_som_b200.distributed import PrototypeShardedSOM, shard_range
     ms, D, B, T = (24, 20), 160, 333, 3.0
     K = ms[0] * ms[1]
     torch.manual_seed(7)                                  # same seed on every rank: identical full-map draw
     layer = PrototypeShardedSOM(make_config(list(ms), D, fcn, Tmax=T)).cuda()
+    if dx_mode != "sync":                                 # asynchronous exchange of the latent gradients
+        layer.async_dx = True
+        layer.dx_overlap = dx_mode                        # "stream": behind the backward launch; "kernel": inside it
     torch.manual_seed(7)
     W_full = torch.rand(K, D)
     if fcn == "cosine":
         W_full = torch.nn.functional.normalize(W_full, p=2, dim=1)
     k0, k1 = shard_range(K, world, rank)
-    x_np = np.random.RandomState(1).randn(B, D).astype(np.float32)
-    x = torch.as_tensor(x_np).cuda().requires_grad_(True)
-    d_loc, bmu = layer(x)
-    loss = layer.som_loss(layer.compute_weights(bmu), d_loc)
-    (loss * 0.5).backward()
-    bmu_only = layer.best_matching_units(x)                # last collective: every check below is local
-    torch.cuda.synchronize()
-    assert torch.equal(layer.prototypes.detach().cpu(), W_full[k0:k1])
-    assert d_loc.shape == (B, k1 - k0)
     pos = O.grid_positions(ms)
-    ref = O.step(x_np, W_full.numpy(), pos, T, fcn, 0.5, np.float64, bmu_override=bmu.cpu().numpy())
-    _, hard, worst = O.classify_bmu_mismatches(x_np, W_full.numpy(), bmu.cpu().numpy(), fcn)
-    assert hard == 0, worst
-    assert O.rel_err(d_loc.detach().cpu().numpy(), ref.distances[:, k0:k1]) < 3e-6
-    assert abs(loss.item() - float(ref.loss)) <= 1e-5 * abs(float(ref.loss))
-    assert O.rel_err(x.grad.cpu().numpy(), ref.grad_x) < 1e-5
-    assert O.rel_err(layer.prototypes.grad.cpu().numpy(), ref.grad_w[k0:k1]) < 1e-5
-    assert torch.equal(bmu, bmu_only)
+    for it in range(3 if dx_mode != "sync" else 1):       # repeated calls: the two symmetric buffers alternate
+        x_np = np.random.RandomState(1 + it).randn(B, D).astype(np.float32)
+        x = torch.as_tensor(x_np).cuda().requires_grad_(True)
+        layer.prototypes.grad = None
+        d_loc, bmu = layer(x)
+        loss = layer.som_loss(layer.compute_weights(bmu), d_loc)
+        (loss * 0.5).backward()
+        layer.wait_dx()
+        bmu_only = layer.best_matching_units(x)            # last collective: every check below is local
+        torch.cuda.synchronize()
+        assert torch.equal(layer.prototypes.detach().cpu(), W_full[k0:k1])
+        assert d_loc.shape == (B, k1 - k0)
+        ref = O.step(x_np, W_full.numpy(), pos, T, fcn, 0.5, np.float64, bmu_override=bmu.cpu().numpy())
+        _, hard, worst = O.classify_bmu_mismatches(x_np, W_full.numpy(), bmu.cpu().numpy(), fcn)
+        assert hard == 0, worst
+        assert O.rel_err(d_loc.detach().cpu().numpy(), ref.distances[:, k0:k1]) < 3e-6
+        assert abs(loss.item() - float(ref.loss)) <= 1e-5 * abs(float(ref.loss))
+        assert O.rel_err(x.grad.cpu().numpy(), ref.grad_x) < 1e-5, f"dx, call {it}, mode {dx_mode}"
+        assert O.rel_err(layer.prototypes.grad.cpu().numpy(), ref.grad_w[k0:k1]) < 1e-5
+        assert torch.equal(bmu, bmu_only)
 
 
 @pytest.mark.parametrize("fcn", ["euclidean", "cosine"])
 def test_prototype_sharded_matches_oracle(fcn):
     spawn(_sharded_worker, fcn)
+
+
+@pytest.mark.parametrize("dx_mode", ["stream", "kernel"])
+def test_prototype_sharded_async_dx_exchange(dx_mode):
+    """The asynchronous exchange of the latent gradients (joined by wait_dx): enqueued behind the backward launch, or
+    started from inside it by the dx-complete counter of the dx-first two-phase schedule."""
+    spawn(_sharded_worker, "euclidean", dx_mode)
 
 
 def _dp_worker(rank, world, fcn):

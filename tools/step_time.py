@@ -109,7 +109,7 @@ def main():
         dx.data_ptr(), D, 0, 0, wsp, wsn, sp()), "dx"), stamps=True)
     timed("GEMM dW+dx fused launch", lambda: chk(L.som_backward_fused(
         r_hi, r_lo, ldd, xs.hi, xs.lo, ws.hi, ws.lo, xs.ld, x.data_ptr(), D, W.data_ptr(), D, row_sum, nrp, col_sum,
-        ncp, xs.aux, ws.aux, g.data_ptr(), B, K, D, mode, dw.data_ptr(), D, 0, dx.data_ptr(), D, 0, None, None,
+        ncp, xs.aux, ws.aux, g.data_ptr(), B, K, D, mode, dw.data_ptr(), D, 0, dx.data_ptr(), D, 0, 0, None, None,
         wsp, wsn, sp()), "bwd"), stamps=True)
     # the fused prototype optimizer step (update + staging): 9 arrays of K x D floats through HBM
     m, v = torch.zeros_like(W), torch.zeros_like(W)

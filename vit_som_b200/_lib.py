@@ -65,7 +65,7 @@ SIGNATURES = {
                                 c_int64, c_int64, c_int64, c_int, _P, c_int64, c_int, c_int, _P, c_int64, _P]),
     "som_backward_fused": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, c_int64, _P, c_int64, _P, c_int64,
                                    _P, c_int64, _P, c_int64, _P, _P, _P, c_int64, c_int64, c_int64, c_int,
-                                   _P, c_int64, c_int, _P, c_int64, c_int, _P, _P, _P, c_int64, _P]),
+                                   _P, c_int64, c_int, _P, c_int64, c_int, c_int, _P, _P, _P, c_int64, _P]),
     "som_stream_wait_value": (c_int, [_P, c_uint32, _P]),
     "som_stream_write_value": (c_int, [_P, c_uint32, _P]),
     "som_adamw_step": (c_int, [_P, c_int64, _P, c_int64, _P, _P, c_int64, c_int64, c_int64, _P, c_double, c_double,

@@ -351,7 +351,7 @@ int pair_kchunk(int kchunk, int passes) { return passes == 3 ? std::max(1, kchun
 
 // CTA-pair launch of one or two GEMMs that share the tile width, the accumulation chunking and the epilogue kind.
 int launch_pair(int epi, const Problem* probs, int nprob, int bn, int sk_workers, int sk_split, int kchunk, int passes,
-                float* ws, int sms, cudaStream_t st) {
+                float* ws, int sms, cudaStream_t st, int sk_ph1 = 0) {
   if (bn % 32 != 0 || bn < 32 || bn > som::MAX_BN_2CTA)
     return fail(SOM_ERR_ARG, "pair tile width must be a multiple of 32 within the kernel's range");
   const int b_rows = bn / 2;                       // rows of the B tile held by one CTA
@@ -391,6 +391,7 @@ int launch_pair(int epi, const Problem* probs, int nprob, int bn, int sk_workers
   g[0].nprob = nprob;
   g[0].sk_workers = ws ? sk_workers : 0;
   g[0].sk_split = g[0].sk_workers > 0 ? sk_split : 0;
+  g[0].sk_ph1 = g[0].sk_split < 0 ? sk_ph1 : 0;
   if (g[0].sk_workers > 0) {
     g[0].sk_flags = reinterpret_cast<unsigned int*>(ws);
     g[0].sk_ws = ws + SK_FLAG_WORDS;
@@ -1735,16 +1736,22 @@ int som_backward_fused(const float* r_hi, const float* r_lo, int64_t ldr, const 
                        const float* W, int64_t ldw, const float* row_part, int64_t n_row_parts, const float* col_part,
                        int64_t n_col_parts, const float* x_aux, const float* w_aux, const float* g_dev, int64_t B,
                        int64_t K, int64_t D, int mode, float* dW, int64_t lddw, int accumulate_dw, float* dx,
-                       int64_t lddx, int sm_limit, unsigned int* dw_done, int64_t* dw_done_expected, float* ws,
+                       int64_t lddx, int sm_limit, int count_dx, unsigned int* done, int64_t* done_expected, float* ws,
                        int64_t ws_floats, void* stream) {
+  unsigned int* dw_done = done;                      // (the counted GEMM is chosen below)
+  int64_t* dw_done_expected = done_expected;
   if (dw_done_expected) *dw_done_expected = -1;
   if (!W || !col_part || !x || !row_part || n_row_parts <= 0 || n_col_parts <= 0 || !g_dev || !dW || !dx || ldw < D ||
       lddw < D || ldx < D || lddx < D)
     return fail(SOM_ERR_ARG, "som_backward_fused: bad argument");
   if (mode != SOM_MODE_EUCLIDEAN && mode != SOM_MODE_COSINE) return fail(SOM_ERR_ARG, "som_backward_fused: bad mode");
   if (mode == SOM_MODE_COSINE && (!w_aux || !x_aux)) return fail(SOM_ERR_ARG, "som_backward_fused: cosine needs the reciprocal norms");
+  // Counted (two-phase) launches use ALL SMs for the first GEMM and at most sm_limit for the second: the pairs beyond
+  // the limit get an empty share of phase 1, exit, and their SMs are free exactly when the exchange kernel that the
+  // first GEMM's completion starts needs them.  Uncounted launches: sm_limit bounds the whole grid.
+  const bool phased = done != nullptr;
   int sms = 0;
-  if (int rc = effective_sms(&sms, sm_limit)) return rc;
+  if (int rc = effective_sms(&sms, phased ? 0 : sm_limit)) return rc;
   if (ws && (reinterpret_cast<uintptr_t>(ws) & 15) != 0) return fail(SOM_ERR_ARG, "workspace must be 16-byte aligned");
   Problem p[2];
   // dW[K,D] = R^T[K,B] . x[B,D]: A = R read MN-major (K contiguous), B = x~ MN-major (D contiguous)
@@ -1762,9 +1769,10 @@ int som_backward_fused(const float* r_hi, const float* r_lo, int64_t ldr, const 
   const int forced_bn = g_bn_override.load();
   const int64_t slots = sms / 2;
   int best_bn = 0; int64_t best_workers = 0; double best_cost = 1e300;
-  // Data parallel (dw_done): two-phase schedule - every pair first works off its share of the dW tiles, then its share
-  // of the dx tiles, so dW is complete (and its exchange can start) after about half of the launch.
-  const bool phased = dw_done != nullptr;
+  // Counted: two-phase schedule - every pair first works off its share of the FIRST GEMM's tiles (dW for data
+  // parallelism, dx for prototype shards), then its share of the other's, so the first result is complete (and its
+  // exchange can start) after about half of the launch.
+  if (phased && count_dx) std::swap(p[0], p[1]);
   if (ws && g_streamk.load() >= 0 && g_cg_override.load() != 1 && B > 128 && K > 128) {
     for (int bn : {256, 192, 128, 64}) {
       if (forced_bn && bn != forced_bn) continue;
@@ -1791,13 +1799,15 @@ int som_backward_fused(const float* r_hi, const float* r_lo, int64_t ldr, const 
     return som_backward_dx(r_hi, r_lo, ldr, w_hi, w_lo, ld_stage, x, ldx, row_part, n_row_parts, x_aux, g_dev, B, K, D,
                            mode, dx, lddx, 0, sm_limit, ws, ws_floats, stream);
   }
+  int ph1 = 0;
   if (dw_done) {
     p[0].e.done_counter = dw_done;
-    // 16 warp slabs (2 CTAs x 8 epilogue warps) per 256 x bn tile of dW, each counted once by the tile's owner
-    if (dw_done_expected) *dw_done_expected = ((K + 255) / 256) * ((D + best_bn - 1) / best_bn) * 16;
+    // 16 warp slabs (2 CTAs x 8 epilogue warps) per 256 x bn tile of the counted GEMM, each counted once by the tile's owner
+    if (dw_done_expected) *dw_done_expected = ((p[0].M + 255) / 256) * ((p[0].N + best_bn - 1) / best_bn) * 16;
+    if (sm_limit >= 2 && sm_limit / 2 < best_workers) ph1 = std::max(1, sm_limit / 2);
   }
   return launch_pair(som::EPI_GRAD, p, 2, best_bn, static_cast<int>(best_workers), phased ? -1 : 0,
-                     pair_kchunk(g_kchunk.load(), 3), 3, ws, sms, as_stream(stream));
+                     pair_kchunk(g_kchunk.load(), 3), 3, ws, sms, as_stream(stream), ph1);
 }
 
 // ---- stream-ordered memory operations (driver API cuStreamWaitValue32 / cuStreamWriteValue32) ---------------------

@@ -238,6 +238,57 @@ class DataParallelSOM:
 # ------------------------------------------------------------------------------------------------------------
 # prototype-sharded
 # ------------------------------------------------------------------------------------------------------------
+class _DxExchange:
+    """Hook object of a prototype shard for ``ops.FusedLossFn.backward`` (asynchronous mode, ``dx_overlap="kernel"``):
+    the fused backward computes the dx tiles FIRST and raises a counter; the exchange of the partial dx sits behind a
+    stream-ordered wait on it and runs on the SMs the second phase (the dW tiles) leaves free - so even the LAST row
+    chunk's exchange is hidden.  ``exchange_*`` return the tensor handed to autograd (complete after ``wait_dx``)."""
+
+    def __init__(self, layer, nv):
+        self.layer, self.nv = layer, nv
+        self.gemm_sm_limit = layer.gemm_sm_limit
+        sms = torch.cuda.get_device_properties(nv["buf"].device).multi_processor_count
+        self.blocks = max(8, min(64, 2 * (sms - self.gemm_sm_limit))) if self.gemm_sm_limit else layer.async_blocks
+
+    def counter_ptr(self):
+        lay = self.layer
+        dev = self.nv["buf"].device
+        if lay._dx_counter is None:
+            lay._dx_counter = torch.zeros(4, device=dev, dtype=torch.int32)
+        lay._comm_stream(dev).wait_stream(torch.cuda.current_stream(dev))       # fork (also joins a graph capture)
+        return lay._dx_counter.data_ptr()
+
+    def _run(self, dx, expected):
+        from . import _lib
+        L, lay, nv = _lib.lib(), self.layer, self.nv
+        dev = dx.device
+        comm = lay._comm_stream(dev)
+        out = torch.empty_like(dx)
+        if expected is None:
+            comm.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(comm):
+            sp = _lib.stream_ptr(dev)
+            if expected is not None:
+                _lib.check(L.som_stream_wait_value(lay._dx_counter.data_ptr(), expected, sp), "som_stream_wait_value")
+            _lib.check(L.som_allreduce_nvls(nv["mc"], nv["flag_ptrs"], nv["n"], nv["rank"], nv["world"], 1.0,
+                                            self.blocks, sp), "som_allreduce_nvls")
+            out.copy_(dx)
+            if expected is not None:
+                _lib.check(L.som_stream_write_value(lay._dx_counter.data_ptr(), 0, sp), "som_stream_write_value")
+        done = torch.cuda.Event()
+        done.record(comm)
+        out.record_stream(comm)
+        nv["pending"] = done
+        lay._dx_events.append(done)
+        return out
+
+    def exchange_counted(self, dx, expected):
+        return self._run(dx, expected)
+
+    def exchange_after(self, dx):
+        return self._run(dx, None)
+
+
 class _ShardedLossFn(torch.autograd.Function):
     """Global loss of a prototype-sharded map as one autograd node over (x, W_shard): local fused loss kernel,
     scalar all-reduce; backward = local gradient GEMMs + all-reduce of the partial dx."""
@@ -259,8 +310,13 @@ class _ShardedLossFn(torch.autograd.Function):
             # of this call may only overwrite it once that exchange and its copy-out are done
             torch.cuda.current_stream(nv["buf"].device).wait_event(nv["pending"])
             nv["pending"] = None
+        if (nv is not None and layer is not None and layer.async_dx and layer.dx_overlap == "kernel"
+                and ctx.needs_input_grad[0] and ctx.x_dtype == torch.float32):
+            ctx.state.dx_hook = _DxExchange(layer, nv)
         grads = ops.FusedLossFn.backward(ctx, g_out)
         dx = grads[0]
+        if ctx.state.dx_exchanged:
+            return grads[:11]                       # exchanged (asynchronously) from inside the fused backward
         if dx is not None:
             if nv is not None and dx.data_ptr() == nv["buf"].data_ptr() and dx.dtype == torch.float32:
                 # partial dx of all shards summed in the NVSwitch (our two-shot multimem kernel), in place in the
@@ -321,6 +377,13 @@ class PrototypeShardedSOM(SOMLayer):
         # leaves of the graph (row-chunked scoring of a large map); leave it off when dx flows on into an encoder.
         self.async_dx = False
         self.async_blocks = 32                # grid of the exchange kernel in asynchronous mode (two blocks per SM)
+        # how the asynchronous exchange overlaps: "stream" - enqueued behind the backward launch, runs under whatever
+        # the compute stream does next (the next row chunk); "kernel" - the fused backward computes the dx tiles first
+        # and its dW half leaves gemm_sm_limit .. 148 SMs to the exchange, which a counter starts (hides the exchange
+        # of a chunk that has no successor, at the price of a second phase on fewer SMs)
+        self.dx_overlap = "stream"
+        self.gemm_sm_limit = 136
+        self._dx_counter = None
         self._dx_events = []
         self._dx_turn = 0
         self._comm = None

@@ -117,7 +117,7 @@ def stage_rows(src: torch.Tensor, mode: int) -> Staging:
 class ForwardState:
     """What one forward leaves behind for the loss and the backward: raw and staged operands and the distances."""
     __slots__ = ("x", "W", "xs", "ws", "mode", "B", "K", "D", "dist_buf", "ldd", "packed", "idx_offset",
-                 "x_in", "W_in", "grad_accum", "dw_out", "dx_out", "nvls_dx", "layer")
+                 "x_in", "W_in", "grad_accum", "dw_out", "dx_out", "nvls_dx", "layer", "dx_hook", "dx_exchanged")
 
 
 def forward(x: torch.Tensor, W: torch.Tensor, mode: int, ws: Staging | None = None, stage_w: bool = True,
@@ -177,6 +177,8 @@ def forward(x: torch.Tensor, W: torch.Tensor, mode: int, ws: Staging | None = No
     st.dx_out = None             # optional caller-owned [B, D] destination of dx (prototype shards: a symmetric buffer)
     st.nvls_dx = None
     st.layer = None
+    st.dx_hook = None            # prototype shards: exchange of dx started by the dx-complete counter of the fused backward
+    st.dx_exchanged = False
     return st, bmu
 
 
@@ -302,7 +304,11 @@ class FusedLossFn(torch.autograd.Function):
         if g.device != dev:
             g = g.to(dev)
         hook = ctx.dw_hook
-        sm_limit = int(getattr(hook, "gemm_sm_limit", 0) or 0) if hook is not None else 0
+        dxh = st.dx_hook                        # at most one of the two results is counted (dW: data parallel, dx: shards)
+        if hook is not None and dxh is not None:
+            raise SomError("a data-parallel dW hook and a prototype-shard dx hook cannot be combined on one layer")
+        counted = hook if hook is not None else dxh
+        sm_limit = int(getattr(counted, "gemm_sm_limit", 0) or 0) if counted is not None else 0
         dx = dw = join = None
         acc_buf = st.grad_accum                 # row-chunked batches: the GEMM epilogue adds into this [K, D] buffer
         nothing = (None,) * 9
@@ -315,18 +321,24 @@ class FusedLossFn(torch.autograd.Function):
                 dw = acc_buf if acc_buf is not None else (
                     st.dw_out if st.dw_out is not None else torch.empty((K, D), device=dev, dtype=torch.float32))
                 dx = st.dx_out if st.dx_out is not None else torch.empty((B, D), device=dev, dtype=torch.float32)
-                counter = hook.counter_ptr() if hook is not None else None
+                counter = counted.counter_ptr() if counted is not None else None
                 expected = ctypes.c_int64(-1)
                 check(_gemm("dw+dx", lambda: L.som_backward_fused(
                     r_hi, r_lo, ctx.ldr, st.xs.hi, st.xs.lo, st.ws.hi, st.ws.lo, st.xs.ld, ptr(st.x), st.x.stride(0),
                     ptr(st.W), st.W.stride(0), row_part, nrp, col_part, ncp, st.xs.aux, st.ws.aux, ptr(g), B, K, D, mode,
-                    ptr(dw), dw.stride(0), 1 if acc_buf is not None else 0, ptr(dx), dx.stride(0), sm_limit, counter,
-                    ctypes.addressof(expected), gws, gws_n, sp)), "som_backward_fused")
+                    ptr(dw), dw.stride(0), 1 if acc_buf is not None else 0, ptr(dx), dx.stride(0), sm_limit,
+                    1 if dxh is not None else 0, counter, ctypes.addressof(expected), gws, gws_n, sp)),
+                    "som_backward_fused")
                 if hook is not None:
                     # data parallel: the exchange of dW starts as soon as its last tile is written (a stream-ordered
                     # wait on the counter the dW epilogues raise), under the dx tiles of the same launch
                     join = (hook.exchange_counted(dw, int(expected.value)) if expected.value >= 0
                             else hook.exchange_after(dw))
+                elif dxh is not None:
+                    # prototype shards: the same with the roles swapped - dx tiles first, their exchange under the dW tiles
+                    dx = (dxh.exchange_counted(dx, int(expected.value)) if expected.value >= 0
+                          else dxh.exchange_after(dx))
+                    st.dx_exchanged = True
                 if acc_buf is not None:
                     dw = None                   # already accumulated in place: nothing for autograd to add
             else:
@@ -347,6 +359,9 @@ class FusedLossFn(torch.autograd.Function):
                         r_hi, r_lo, ctx.ldr, st.ws.hi, st.ws.lo, st.ws.ld, ptr(st.x), st.x.stride(0), row_part, nrp,
                         st.xs.aux, ptr(g), B, K, D, mode, ptr(dx), dx.stride(0), 0, sm_limit if join is not None else 0,
                         gws, gws_n, sp)), "som_backward_dx")
+                    if dxh is not None:
+                        dx = dxh.exchange_after(dx)
+                        st.dx_exchanged = True
             if dx is not None:
                 if dx.dtype != ctx.x_dtype:
                     dx = dx.to(ctx.x_dtype)
