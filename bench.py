@@ -318,6 +318,7 @@ def measure_som(env, name, wl, steps, warmup, sharded=False, with_e2e=False, wit
         torch.manual_seed(1234)                # identical full-map draw on every rank, each keeps its block
         layer = PrototypeShardedSOM(make_cfg(ms, D, fcn, T)).to(dev)
         layer.async_dx = not args.sync_dx      # the dx exchange of a row chunk runs under the next chunk's kernels
+        layer.async_loss = not args.sync_dx    # and the scalar loss sum leaves the critical path (joined by wait_dx)
         torch.manual_seed(4321)                # replicated latents
     else:
         torch.manual_seed(1234 + rank)
@@ -344,6 +345,10 @@ def measure_som(env, name, wl, steps, warmup, sharded=False, with_e2e=False, wit
         if chunked:
             dp.detach()                        # chunked + data parallel: one exchange of the accumulated gradient
 
+    # (worth its price - a second phase on 136 SMs - when the exchange of one chunk takes longer than ~60 us at the
+    # NVSwitch's all-reduce rate of ~274 GB/s, i.e. from 4 GPUs up at config 5)
+    kernel_last = sharded and not args.no_kernel_overlap and chunk * D * 4 / 274e3 > 60.0
+
     def hot_path(xs):
         """One step through the public module API (vit_som.py:82-86 call sequence + backward) over all row chunks."""
         layer.invalidate_staging()             # prototypes change every training step: their staging is in the step
@@ -364,7 +369,7 @@ def measure_som(env, name, wl, steps, warmup, sharded=False, with_e2e=False, wit
             if sharded and layer.async_dx:
                 # the last row chunk has no successor to hide its dx exchange under: its backward computes the dx tiles
                 # first and the exchange runs beside the dW tiles of the same launch
-                layer.dx_overlap = "kernel" if i == len(xs) - 1 and not args.no_kernel_overlap else "stream"
+                layer.dx_overlap = "kernel" if i == len(xs) - 1 and kernel_last else "stream"
             d, bmu = layer(x)
             loss = layer.som_loss(layer.compute_weights(bmu), d)
             loss.backward()

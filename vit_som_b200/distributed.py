@@ -299,6 +299,20 @@ class _ShardedLossFn(torch.autograd.Function):
                                        grid_dims)
         ctx.group = group
         ctx.nvls = getattr(state, "nvls_dx", None)
+        layer = getattr(state, "layer", None)
+        if layer is not None and layer.async_loss and loss.is_cuda:
+            # the scalar all-reduce leaves the compute stream's critical path: the VALUE of the loss is complete after
+            # wait_dx() (backward does not need it - its upstream gradient is independent of the loss value)
+            cur = torch.cuda.current_stream(loss.device)
+            comm = layer._comm_stream(loss.device)
+            comm.wait_stream(cur)
+            with torch.cuda.stream(comm):
+                all_reduce_sum(loss, group)
+            done = torch.cuda.Event()
+            done.record(comm)
+            loss.record_stream(comm)
+            layer._dx_events.append(done)
+            return loss
         return all_reduce_sum(loss, group)
 
     @staticmethod
@@ -382,6 +396,9 @@ class PrototypeShardedSOM(SOMLayer):
         # and its dW half leaves gemm_sm_limit .. 148 SMs to the exchange, which a counter starts (hides the exchange
         # of a chunk that has no successor, at the price of a second phase on fewer SMs)
         self.dx_overlap = "stream"
+        # asynchronous sum of the scalar loss over the shards (opt-in): som_loss returns at once, the returned tensor
+        # holds the global loss only after wait_dx() - do not compute with it on the device before that
+        self.async_loss = False
         self.gemm_sm_limit = 136
         self._dx_counter = None
         self._dx_events = []
