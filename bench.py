@@ -707,6 +707,31 @@ def parity_check(env):
                           "dx_rel": rel(xs.grad.cpu().numpy(), refs.grad_x),
                           "dw_shard_rel": rel(sh.prototypes.grad.cpu().numpy(), refs.grad_w[k0:k1])}
         ok &= hard == 0 and max(res["sharded"]["loss_rel"], res["sharded"]["dx_rel"], res["sharded"]["dw_shard_rel"]) < 1e-5
+        # (4) the same layer the way the cfg5 record runs it: two row chunks, in-place dW accumulation, asynchronous loss
+        # sum and dx exchange - the first chunk's behind its backward launch, the last chunk's from inside it
+        sh.async_dx = sh.async_loss = True
+        sh.batch_rows = B
+        sh.grad_accumulator = torch.zeros_like(sh.prototypes)
+        sh.prototypes.grad = None
+        half = B // 2
+        xa = [torch.as_tensor(x_np[r0:r0 + half]).to(dev).requires_grad_(True) for r0 in (0, half)]
+        losses, bmus = [], []
+        for i, xc in enumerate(xa):
+            sh.dx_overlap = "kernel" if i == 1 else "stream"
+            d_c, bmu_c = sh(xc)
+            loss_c = sh.som_loss(sh.compute_weights(bmu_c), d_c)
+            loss_c.backward()
+            losses.append(loss_c)
+            bmus.append(bmu_c)
+        sh.wait_dx()
+        torch.cuda.synchronize(dev)
+        bmu_a = torch.cat(bmus).cpu().numpy()
+        refa = O.step(x_np, W, pos, T, "euclidean", 1.0, np.float64, bmu_override=bmu_a)
+        loss_a = float(sum(l.item() for l in losses))
+        res["sharded_async"] = {"loss_rel": abs(loss_a - float(refa.loss)) / abs(float(refa.loss)),
+                                "dx_rel": rel(torch.cat([xc.grad for xc in xa]).cpu().numpy(), refa.grad_x),
+                                "dw_shard_rel": rel(sh.grad_accumulator.cpu().numpy(), refa.grad_w[k0:k1])}
+        ok &= max(res["sharded_async"].values()) < 1e-5
         del sh
     res["ok"] = env.max_over_ranks(0.0 if ok else 1.0)[0] == 0.0
     res["shape"] = {"B": B, "K": K, "D": D, "T": T, "distance": "euclidean"}
