@@ -642,7 +642,9 @@ def parity_check(env):
     from oracle import som_oracle as O
     from vit_som_b200 import SOMLayer
     world, rank, dev = env.world, env.rank, env.dev
-    ms, D, B, T = (24, 20), 192, 256 * world, 3.0            # > 128 local rows: the fused CTA-pair backward is the path checked
+    # > 128 local rows and > 128 local prototypes at up to 8 GPUs: the fused CTA-pair backward (and its counted,
+    # two-phase variant) is the path that is checked
+    ms, D, B, T = (40, 32), 192, 256 * world, 3.0
     K = ms[0] * ms[1]
     pos = O.grid_positions(ms)
     res, ok = {}, True
