@@ -880,10 +880,9 @@ def main():
     if not args.no_extras:
         try:
             parity = parity_check(env)
-        except Exception as exc:  # noqa: BLE001
+        except Exception as exc:  # noqa: BLE001  (recorded in the line; the timed measurements still run)
             parity = {"ok": False, "error": repr(exc)}
-            if world > 1:
-                raise
+            print(f"bench: parity check failed ({exc!r})", file=sys.stderr)
 
     env.clocks.__enter__()                      # sampling from the warm-up on; stopped at the end of the timed region
     head = measure_som(env, args.workload, wl, args.steps, args.warmup, sharded=sharded, with_e2e=True,
@@ -908,8 +907,7 @@ def main():
                 try:
                     vit[tag] = measure_vit_som(env, tag, dataset, msz, bsz, 20, 5)
                 except Exception as exc:  # noqa: BLE001
-                    if world > 1:
-                        raise
+                    print(f"bench: ViT-SOM {tag} failed ({exc!r})", file=sys.stderr)
                     vit[tag] = {"error": repr(exc)}
             # share of the SOM layer: the SOM step of the same shape (cosine, as the YAMLs select), timed standalone
             if world == 1:

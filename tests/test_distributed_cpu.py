@@ -156,3 +156,29 @@ def _dp_worker(rank, world, fcn):
 @pytest.mark.parametrize("fcn", ["euclidean", "cosine"])
 def test_data_parallel_gradient_average_world2(fcn):
     spawn(_dp_worker, fcn)
+
+
+def _bucket_worker(rank, world):
+    """FlatGradBucket (vit_som.py): gradients are views of one flat buffer, one all-reduce averages all of them."""
+    from vit_som_b200.vit_som import FlatGradBucket
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(5, 3)
+    frozen = torch.nn.Parameter(torch.zeros(2), requires_grad=False)
+    bucket = FlatGradBucket(list(lin.parameters()) + [frozen])
+    assert bucket.flat.numel() == 5 * 3 + 3 and frozen.grad is None
+    assert lin.weight.grad.data_ptr() == bucket.flat.data_ptr()
+    for step in range(2):
+        bucket.zero()
+        x = torch.full((4, 5), float(rank + 1 + step))
+        lin(x).sum().backward()                             # autograd accumulates INTO the views
+        assert lin.weight.grad.data_ptr() == bucket.flat.data_ptr()
+        local = bucket.flat.clone()
+        bucket.all_reduce_mean()
+        gathered = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(gathered, local)
+        assert torch.allclose(bucket.flat, torch.stack(gathered).mean(0))
+        assert torch.allclose(lin.bias.grad, torch.full((3,), 4.0))
+
+
+def test_flat_grad_bucket_world2():
+    spawn(_bucket_worker)

@@ -177,3 +177,34 @@ def _dp_repeat_worker(rank, world, mode):
 @pytest.mark.parametrize("mode", ["auto", "nccl"])
 def test_data_parallel_repeated_steps(mode):
     spawn(_dp_repeat_worker, mode)
+
+
+def test_layer_on_a_device_that_is_not_current():
+    """Single process, two GPUs: the layer lives on cuda:1 while cuda:0 is the current device - every wrapper must run
+    on the tensors' device and that device's current stream (round-1 finding: launches went to the current device)."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from vit_som_b200 import FusedPrototypeAdamW, SOMLayer
+    torch.cuda.set_device(0)
+    ms, D, B, T = (12, 16), 200, 300, 2.0
+    torch.manual_seed(3)
+    layer = SOMLayer(make_config(list(ms), D, "euclidean", Tmax=T)).to("cuda:1")
+    opt = FusedPrototypeAdamW(layer, lr=1e-3)
+    x_np = np.random.RandomState(4).randn(B, D).astype(np.float32)
+    x = torch.as_tensor(x_np).to("cuda:1").requires_grad_(True)
+    assert torch.cuda.current_device() == 0
+    d, bmu = layer(x)
+    loss = layer.som_loss(layer.compute_weights(bmu), d)
+    loss.backward()
+    W = layer.prototypes.detach().cpu().numpy()
+    torch.cuda.synchronize("cuda:1")
+    assert d.device.index == 1 and x.grad.device.index == 1 and torch.cuda.current_device() == 0
+    ref = O.step(x_np, W, O.grid_positions(ms), T, "euclidean", 1.0, np.float64, bmu_override=bmu.cpu().numpy())
+    assert abs(loss.item() - float(ref.loss)) <= 1e-5 * abs(float(ref.loss))
+    assert O.rel_err(x.grad.cpu().numpy(), ref.grad_x) < 1e-5
+    assert O.rel_err(layer.prototypes.grad.cpu().numpy(), ref.grad_w) < 1e-5
+    opt.step()                                               # the optimizer kernel on cuda:1 as well
+    torch.cuda.synchronize("cuda:1")
+    assert not np.array_equal(layer.prototypes.detach().cpu().numpy(), W)
+    w = layer.compute_weights(bmu).materialize()
+    assert w.device.index == 1
