@@ -95,7 +95,7 @@ class DataParallelSOM:
       so it runs under the dx half of the same launch;
     * ``"after"``: one fused launch, exchange after it (no overlap; the baseline of the other two).
 
-    Measured, config 2 (dW = 20 MB), ms per step at 1 / 2 / 8 GPUs: split 0.197 / 0.240 / 0.239, counter 0.197 / 0.248 /
+    Measured, config 2 (dW = 20 MB), ms per step at 1 / 2 / 8 GPUs: split 0.199 / 0.240 / 0.240, counter 0.199 / 0.248 /
     0.245, after - / 0.289 / -.  The exchange itself takes 75-80 us at any GPU count (two-shot NVLS all-reduce at the
     NVSwitch's rate, 274 GB/s algorithm bandwidth) and cannot start before dW is complete (~65-75 us into the backward),
     which bounds the step of this layer-only benchmark at ~0.23 ms; in ViT-SOM training it hides under the ViT backward."""
