@@ -17,6 +17,8 @@
 #include <cudaTypedefs.h>
 #include <algorithm>
 #include <atomic>
+#include <map>
+#include <mutex>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -323,9 +325,46 @@ int launch_single_t(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CU
   return SOM_OK;
 }
 
+// CTA pairs of the pair kernel that can be resident at the same time on the current device (per shared-memory size;
+// cached).  The in-kernel hand-over of split-K / stream-K partial tiles needs every pair of the grid to be resident -
+// an owner spins on flags that a not-yet-scheduled pair would have to raise - so schedules with more workers than this
+// are not launched (MPS SM shares, green contexts or another resident kernel's shared memory can lower it below 74).
+template <int EPI>
+int resident_pairs(size_t smem, int* out) {
+  static std::mutex mu;
+  static std::map<std::pair<int, size_t>, int> cache;
+  int dev = 0;
+  SOM_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find({dev, smem});
+  if (it == cache.end()) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * 1024); cfg.blockDim = dim3(som::NUM_THREADS_2CTA); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    SOM_CUDA(cudaFuncSetAttribute(som::som_gemm3x_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  som::SMEM_LIMIT));
+    SOM_CUDA(cudaOccupancyMaxActiveClusters(&n, som::som_gemm3x_pair_kernel<EPI>, &cfg));
+    it = cache.emplace(std::make_pair(dev, smem), n).first;
+  }
+  *out = it->second;
+  return SOM_OK;
+}
+
 template <int EPI>
 int launch_pair_t(const som::PairMaps& m0, const som::PairMaps& m1, const som::GemmShape& g0, const som::EpiParams& e0,
                   const som::GemmShape& g1, const som::EpiParams& e1, int grid, size_t smem, cudaStream_t st) {
+  if (g0.sk_workers > 0) {
+    int resident = 0;
+    if (int rc = resident_pairs<EPI>(smem, &resident)) return rc;
+    if (g0.sk_workers > resident)
+      return fail(SOM_ERR_ARG, "split-K / stream-K schedule of " + std::to_string(g0.sk_workers) + " CTA pairs, but only " +
+                                   std::to_string(resident) + " can be resident on this device right now (SM share too "
+                                   "small?): pass a smaller sm_limit or no workspace");
+  }
   static std::atomic<bool> attr_set[kMaxDevices];
   int dev = 0;
   SOM_CUDA(cudaGetDevice(&dev));
@@ -415,6 +454,11 @@ int launch_pair(int epi, const Problem* probs, int nprob, int bn, int sk_workers
 int effective_sms(int* sms, int sm_limit = 0) {
   DeviceInfo di;
   if (int rc = device_info(di)) return rc;
+  // never plan for more CTA pairs than can be resident together (an MPS SM share or a green context can make that fewer
+  // than SMs / 2): the schedulers below hand partial tiles over between resident pairs
+  int resident = 0;
+  if (int rc = resident_pairs<som::EPI_GRAD>(som::SMEM_LIMIT, &resident)) return rc;
+  if (resident >= 1 && 2 * resident < di.sms) di.sms = 2 * resident;
   if (sm_limit >= 2 && sm_limit < di.sms) di.sms = sm_limit & ~1;
   *sms = di.sms;
   return SOM_OK;
