@@ -39,6 +39,22 @@ extern "C" {
 
 #define SOM_MODE_EUCLIDEAN 0
 #define SOM_MODE_COSINE    1
+/*
+ * Operand precision, OR-ed into every `mode` argument (all calls of one forward / loss / backward must agree):
+ *   0 (default)      3xTF32: staged operands are exact tf32 values in fp32 containers (hi, lo), tcgen05.mma.kind::tf32
+ *   SOM_PREC_FP16X3  3xFP16: staged operands are fp16 hi/lo pairs of the ROW-SCALED matrix (each row times the power of
+ *                    two that lifts its largest magnitude into [2^14, 2^15)), tcgen05.mma.kind::f16 - the same three
+ *                    products hi.hi + hi.lo + lo.hi, the same 22-bit operand split and fp32 accumulation, at twice the
+ *                    tensor-core rate and half the operand bytes.  The scales are exact powers of two; the epilogues take
+ *                    them out again.  In this mode
+ *                      - hi / lo / r_hi / r_lo point to __half matrices (passed through the float pointers), their
+ *                        leading dimensions count halves and must be multiples of 8;
+ *                      - an aux vector holds 3 * rows + 4 floats: aux | 2^-e | 2^e | 4 statistics words;
+ *                      - row_part / col_part need 4 more floats each (1 / S of the staged R, see som_loss_fused);
+ *                      - som_forward / som_bmu_decode_scaled also produce the statistic the loss kernel scales R with.
+ *                    The general-path entry points (som_bwd_coeffs, som_bwd_dx, som_bwd_dw) take tf32 stagings only.
+ */
+#define SOM_PREC_FP16X3    16
 
 #define SOM_OK             0
 #define SOM_ERR_ARG       -1   /* bad argument (null pointer, misalignment, unsupported size)   */
@@ -103,6 +119,17 @@ int som_fwd_distances(const float* x_hi, const float* x_lo, int64_t ldx, const f
 /* bmu[b] = low 32 bits of packed[b] (clamped to [0, K_total)), optional min_key[b] = winning key. */
 int som_bmu_decode(const long long* packed, int64_t B, int64_t K_total,
                    int64_t* bmu, float* min_key, void* stream);
+
+/*
+ * SOM_PREC_FP16X3 only: som_bmu_decode plus the batch statistic of the backward staging.  The loss kernel stages
+ *   R^[b,k] = R_unit[b,k] * 2^-e_b * 2^-g_k * S      (2^e_b, 2^g_k: the row scales of the staged latents / prototypes)
+ * with ONE power of two S per call, chosen from  stat = max_b(2^-e_b / d_bmu(b)) * max_k 2^-g_k  (cosine: without the
+ * 1 / d) so that R^ stays below 2^14; stat is left in x_aux[3 B] (zeroed by the staging kernel of the same forward).
+ *   x_aux [3 B + 4], w_aux [3 K + 4]: aux vectors of this forward's stagings; K = prototypes staged on this rank.
+ * Prototype shards call it after the (key, index) minima have been reduced across the ranks.  bmu / min_key may be NULL.
+ */
+int som_bmu_decode_scaled(const long long* packed, int64_t B, int64_t K_total, int64_t* bmu, float* min_key,
+                          float* x_aux, const float* w_aux, int64_t K, int mode, void* stream);
 
 /*
  * Gaussian neighbourhood weights w[b,k] = exp(-|p_k - p_bmu(b)|^2 / (2 T^2)), materialised.
@@ -189,6 +216,9 @@ int som_forward(const float* x, int64_t ldx, const float* W, int64_t ldw,
  * table (a few ulp from the reference's exp(-(sqrt(dr^2+dc^2))^2 / 2T^2)).  Pass 0, 0 for any other grid (hexa).
  * The upstream gradient of the loss is applied later, in the epilogue of the gradient GEMMs.
  * scratch: at least som_loss_fused_scratch_floats(B, K) floats, word 0 zero on entry (restored on exit).
+ * x_aux / w_aux: aux vectors of the forward's stagings; read in SOM_PREC_FP16X3 mode only (NULL otherwise), where R is
+ * staged as the fp16 hi/lo split of R_unit * 2^-e_b * 2^-g_k * S (see som_bmu_decode_scaled; values that would leave
+ * the fp16 range saturate at 60000) and 1 / S is stored at row_part[B * n_row_parts] and col_part[n_col_parts * K].
  */
 int64_t som_loss_fused_scratch_floats(int64_t B, int64_t K);
 int som_loss_fused_parts(int64_t B, int64_t K, int64_t* n_row_parts, int64_t* n_col_parts);
@@ -196,7 +226,7 @@ int som_loss_fused(const float* dist, int64_t ldd, const int64_t* bmu, const flo
                    int grid_rows, int grid_cols,
                    int64_t B, int64_t K, int64_t k_offset, const float* T_dev, float inv_count, int mode,
                    float* r_hi, float* r_lo, int64_t ldr, float* row_part, float* col_part,
-                   float* scratch, float* loss_out, void* stream);
+                   float* scratch, float* loss_out, const float* x_aux, const float* w_aux, void* stream);
 
 /*
  * The two gradient GEMMs of the closed-form backward (ATen _euclidean_dist_backward | MmBackward0 +
@@ -290,6 +320,13 @@ int som_debug_gemm(const float* a_hi, const float* a_lo, int64_t lda, int a_mn,
                    const float* b_hi, const float* b_lo, int64_t ldb, int b_mn,
                    int64_t M, int64_t N, int64_t Kred, int bn, int kchunk, int passes,
                    float* C, int64_t ldc, float* ws, int64_t ws_floats, void* stream);
+
+/* The same mainloop in 3xFP16: hi / lo are __half matrices (no row scaling here), lda / ldb in halves (multiples of 8),
+ * k-blocks of 64; bn must be a multiple of 128 when an MN-major B is read by CTA pairs. */
+int som_debug_gemm_f16(const void* a_hi, const void* a_lo, int64_t lda, int a_mn,
+                       const void* b_hi, const void* b_lo, int64_t ldb, int b_mn,
+                       int64_t M, int64_t N, int64_t Kred, int bn, int kchunk, int passes,
+                       float* C, int64_t ldc, float* ws, int64_t ws_floats, void* stream);
 
 /* Diagnostics, host only: the work decomposition of the CTA-pair kernel for `workers` CTA pairs over the k-block units
  * of one or two GEMMs (tiles x k-blocks each; tiles1 = 0 for one GEMM).  split > 0: tile-aligned split-K, 0: even

@@ -114,7 +114,7 @@ def test_integration_doc_cpp_stub_matches_the_header():
 
 
 def test_abi_version_and_pure_host_entry_points(lib):
-    assert lib.som_b200_abi_version() == 6
+    assert lib.som_b200_abi_version() == 7
     assert lib.som_gemm_workspace_floats() == 4096 + 2 * 74 * 256 * 256  # 74 CTA pairs (a B200, and the GPU-less default), two slots each
     assert lib.som_loss_scratch_floats(1024, 1600) >= 1024 * 2
     assert lib.som_loss_fused_scratch_floats(1024, 1600) == (1024 // 8) * 4 + 2

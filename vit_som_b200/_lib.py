@@ -58,7 +58,10 @@ SIGNATURES = {
     "som_loss_fused_scratch_floats": (c_int64, [c_int64, c_int64]),
     "som_loss_fused_parts": (c_int, [c_int64, c_int64, _P, _P]),
     "som_loss_fused": (c_int, [_P, c_int64, _P, _P, c_int, c_int, c_int64, c_int64, c_int64, _P, c_float, c_int,
-                               _P, _P, c_int64, _P, _P, _P, _P, _P]),
+                               _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P]),
+    "som_bmu_decode_scaled": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P, c_int64, c_int, _P]),
+    "som_debug_gemm_f16": (c_int, [_P, _P, c_int64, c_int, _P, _P, c_int64, c_int, c_int64, c_int64, c_int64,
+                                   c_int, c_int, c_int, _P, c_int64, _P, c_int64, _P]),
     "som_backward_dw": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, c_int64, _P, c_int64, _P, _P,
                                 c_int64, c_int64, c_int64, c_int, _P, c_int64, c_int, c_int, _P, c_int64, _P]),
     "som_backward_dx": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, c_int64, _P, c_int64, _P, _P,

@@ -15,6 +15,7 @@
 #include "som_gemm.cuh"
 
 #include <cudaTypedefs.h>
+#include <cuda_fp16.h>
 #include <algorithm>
 #include <atomic>
 #include <map>
@@ -40,6 +41,10 @@ int fail(int code, const std::string& msg) {
   g_last_error = msg;
   return code;
 }
+// `mode` arguments carry the distance (bit 0: euclidean / cosine) and the operand precision (SOM_PREC_FP16X3)
+inline bool mode_ok(int mode) { return (mode & ~(1 | SOM_PREC_FP16X3)) == 0; }
+inline int mode_f16(int mode) { return (mode & SOM_PREC_FP16X3) ? 1 : 0; }
+
 #define SOM_CUDA(call)                                                                              \
   do {                                                                                              \
     cudaError_t err__ = (call);                                                                     \
@@ -101,41 +106,48 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   return fn;
 }
 
-// 2-D fp32 tensor map: `inner` contiguous elements per row, `outer` rows, row pitch ld elements,
-// box = 32 x box_outer, zero fill outside the tensor.  K-major operands use the 128-byte swizzle with 16-byte
-// atoms; MN-major tf32 operands need the 32-byte-atom variant (matches UMMA SWIZZLE_128B_BASE32B).
+// 2-D tensor map of an operand matrix (fp32 containers holding tf32 values, or fp16 when `f16`): `inner` contiguous
+// elements per row, `outer` rows, row pitch ld elements, box = one 128-byte span (32 fp32 / 64 fp16) x box_outer, zero
+// fill outside the tensor.  K-major operands use the 128-byte swizzle with 16-byte atoms; so do MN-major fp16 operands
+// (box = 64 mn x 64 k: the canonical SWIZZLE_128B MN-major panel); MN-major tf32 operands need the 32-byte-atom variant
+// (matches UMMA SWIZZLE_128B_BASE32B).
 int make_tmap(CUtensorMap* map, const float* ptr, int64_t inner, int64_t outer, int64_t ld, int box_outer,
-              bool mn_major = false) {
+              bool mn_major = false, int f16 = 0) {
   auto enc = get_encode();
   if (!enc) return fail(SOM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld & 3) != 0)
-    return fail(SOM_ERR_ARG, "TMA operand must be 16-byte aligned with a leading dimension that is a multiple of 4");
+  const int64_t ld_mask = f16 ? 7 : 3;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld & ld_mask) != 0)
+    return fail(SOM_ERR_ARG, "TMA operand must be 16-byte aligned with a 16-byte multiple as row pitch");
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
-  cuuint32_t box[2] = {32u, static_cast<cuuint32_t>(box_outer)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * (f16 ? 2 : 4)};
+  cuuint32_t box[2] = {f16 ? 64u : 32u, static_cast<cuuint32_t>(box_outer)};
   cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+  CUresult r = enc(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr),
+                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   (mn_major && !f16) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(SOM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(r));
   return SOM_OK;
 }
 
-// 3-D view of an MN-major operand stored [Kred rows][mn columns] (row pitch ld): {32 columns of a panel, k, panel}.
-// One TMA operation then brings `panels` 32 x 32 panels of a tile (a 2-D map needs one operation per panel).  Only
-// for mn % 32 == 0: the panel dimension must be exact for out-of-bounds panels to be zero filled.
-int make_tmap_mn3d(CUtensorMap* map, const float* ptr, int64_t mn, int64_t kred, int64_t ld, int panels) {
+// 3-D view of an MN-major operand stored [Kred rows][mn columns] (row pitch ld): {columns of a panel, k, panel} with
+// panels of 32 (tf32) or 64 (fp16) columns.  One TMA operation then brings `panels` panels of a tile (a 2-D map needs
+// one operation per panel).  Only for mn % panel == 0: the panel dimension must be exact for out-of-bounds panels to
+// be zero filled.
+int make_tmap_mn3d(CUtensorMap* map, const float* ptr, int64_t mn, int64_t kred, int64_t ld, int panels, int f16 = 0) {
   auto enc = get_encode();
   if (!enc) return fail(SOM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld & 3) != 0 || (mn & 31) != 0)
-    return fail(SOM_ERR_ARG, "3-D TMA operand must be 16-byte aligned, ld % 4 == 0, extent % 32 == 0");
-  cuuint64_t dims[3] = {32u, static_cast<cuuint64_t>(kred), static_cast<cuuint64_t>(mn / 32)};
-  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 4, 128u};
-  cuuint32_t box[3] = {32u, 32u, static_cast<cuuint32_t>(panels)};
+  const int64_t pmn = som::gemm_panel_mn(f16), ld_mask = f16 ? 7 : 3;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld & ld_mask) != 0 || (mn % pmn) != 0)
+    return fail(SOM_ERR_ARG, "3-D TMA operand must be 16-byte aligned, row pitch a 16-byte multiple, extent a whole number of panels");
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(pmn), static_cast<cuuint64_t>(kred), static_cast<cuuint64_t>(mn / pmn)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * (f16 ? 2 : 4), 128u};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(pmn), static_cast<cuuint32_t>(som::gemm_bk(f16)), static_cast<cuuint32_t>(panels)};
   cuuint32_t estr[3] = {1u, 1u, 1u};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  CUresult r = enc(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr),
+                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   f16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(SOM_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed with CUresult " + std::to_string(r));
   return SOM_OK;
@@ -189,19 +201,21 @@ double streamk_cost_ns(int64_t units, int64_t workers, int64_t nkb_typ, int bn, 
          t_epi + (segs - 1.0) * t_epi * 0.25 + 4000.0 + 2000.0 + handover;
 }
 
-TileChoice pick_tile(int64_t M, int64_t N, int64_t Kred, int sms, int b_mn, int64_t ws_floats, int bn_req) {
+TileChoice pick_tile(int64_t M, int64_t N, int64_t Kred, int sms, int b_mn, int64_t ws_floats, int bn_req, int f16 = 0) {
   const int forced_bn = bn_req > 0 ? bn_req : g_bn_override.load();
   const int forced_cg = g_cg_override.load();
   const int forced_sk = g_streamk.load();            // -1 = never, 0 = cost model, 1 = whenever possible
-  const int64_t nkb = (Kred + som::BK - 1) / som::BK;
+  // (a k-block costs the same in both precisions: 12 instructions and the same operand bytes; fp16 k-blocks are 64 deep)
+  const int64_t nkb = (Kred + som::gemm_bk(f16) - 1) / som::gemm_bk(f16);
+  const int pmn = som::gemm_panel_mn(f16);
   TileChoice best{1, 128, 0, 0};
   double best_cost = 1e300;
   // MN-major B read panel by panel (no 3-D tensor map: extent not a multiple of 32, single-CTA kernel, or switched off)
   auto consider = [&](int cg, int bn) {
-    const bool panel_loads = b_mn != 0 && (cg == 1 || N % 32 != 0 || (bn / 2) % 32 != 0 || !g_tma3d.load());
+    const bool panel_loads = b_mn != 0 && (cg == 1 || N % pmn != 0 || (bn / 2) % pmn != 0 || !g_tma3d.load());
     if (forced_cg && cg != forced_cg) return;
     if (forced_bn && bn != forced_bn) return;
-    if (cg == 2 && b_mn && (bn / 2) % 32 != 0) return;
+    if (cg == 2 && b_mn && (bn / 2) % pmn != 0) return;
     const int64_t tiles = ((M + 128 * cg - 1) / (128 * cg)) * ((N + bn - 1) / bn);
     const int64_t slots = sms / cg;
     // epilogue of one tile: ~1.5 us + 0.08 us per column a warp drains (measured, instruction-latency bound); it hides
@@ -271,6 +285,7 @@ struct Problem {
   const float* b_hi; const float* b_lo; int64_t ldb; int b_mn;
   int64_t M, N, Kred;
   som::EpiParams e;
+  int f16 = 0;       // operands are fp16 matrices (passed through the float pointers), pitches in fp16 elements
 };
 
 int check_problem(const Problem& p, int passes) {
@@ -280,16 +295,17 @@ int check_problem(const Problem& p, int passes) {
   return SOM_OK;
 }
 
-// Tensor maps of one problem: A boxes of `a_rows` rows, B boxes of `b_rows` rows (K-major) or 32 x 32 panels (MN-major).
+// Tensor maps of one problem: A boxes of `a_rows` rows, B boxes of `b_rows` rows (K-major) or panels (MN-major).
 int make_problem_maps(const Problem& p, int a_rows, int b_rows, CUtensorMap* a_hi, CUtensorMap* a_lo, CUtensorMap* b_hi,
                       CUtensorMap* b_lo) {
   int rc;
   const float* alo = p.a_lo ? p.a_lo : p.a_hi;
   const float* blo = p.b_lo ? p.b_lo : p.b_hi;
-  if (p.a_mn) { if ((rc = make_tmap(a_hi, p.a_hi, p.M, p.Kred, p.lda, 32, true))) return rc; if ((rc = make_tmap(a_lo, alo, p.M, p.Kred, p.lda, 32, true))) return rc; }
-  else        { if ((rc = make_tmap(a_hi, p.a_hi, p.Kred, p.M, p.lda, a_rows))) return rc; if ((rc = make_tmap(a_lo, alo, p.Kred, p.M, p.lda, a_rows))) return rc; }
-  if (p.b_mn) { if ((rc = make_tmap(b_hi, p.b_hi, p.N, p.Kred, p.ldb, 32, true))) return rc; if ((rc = make_tmap(b_lo, blo, p.N, p.Kred, p.ldb, 32, true))) return rc; }
-  else        { if ((rc = make_tmap(b_hi, p.b_hi, p.Kred, p.N, p.ldb, b_rows))) return rc; if ((rc = make_tmap(b_lo, blo, p.Kred, p.N, p.ldb, b_rows))) return rc; }
+  const int f = p.f16, bk = som::gemm_bk(f);
+  if (p.a_mn) { if ((rc = make_tmap(a_hi, p.a_hi, p.M, p.Kred, p.lda, bk, true, f))) return rc; if ((rc = make_tmap(a_lo, alo, p.M, p.Kred, p.lda, bk, true, f))) return rc; }
+  else        { if ((rc = make_tmap(a_hi, p.a_hi, p.Kred, p.M, p.lda, a_rows, false, f))) return rc; if ((rc = make_tmap(a_lo, alo, p.Kred, p.M, p.lda, a_rows, false, f))) return rc; }
+  if (p.b_mn) { if ((rc = make_tmap(b_hi, p.b_hi, p.N, p.Kred, p.ldb, bk, true, f))) return rc; if ((rc = make_tmap(b_lo, blo, p.N, p.Kred, p.ldb, bk, true, f))) return rc; }
+  else        { if ((rc = make_tmap(b_hi, p.b_hi, p.Kred, p.N, p.ldb, b_rows, false, f))) return rc; if ((rc = make_tmap(b_lo, blo, p.Kred, p.N, p.ldb, b_rows, false, f))) return rc; }
   return SOM_OK;
 }
 
@@ -297,7 +313,7 @@ void fill_shape(som::GemmShape& g, const Problem& p, int cg, int bn, int kchunk,
   g = som::GemmShape{};
   g.M = static_cast<int>(p.M); g.N = static_cast<int>(p.N); g.Kred = static_cast<int>(p.Kred);
   g.bn = bn; g.a_mn = p.a_mn ? 1 : 0; g.b_mn = p.b_mn ? 1 : 0;
-  g.kchunk = kchunk; g.passes = passes; g.nprob = 1;
+  g.kchunk = kchunk; g.passes = passes; g.nprob = 1; g.f16 = p.f16;
   g.debug = g_debug.load();
   g.dbg_times = g_dbg_times.load();
   g.tiles_m = static_cast<int>((p.M + som::BM * cg - 1) / (som::BM * cg));
@@ -394,9 +410,14 @@ int launch_pair(int epi, const Problem* probs, int nprob, int bn, int sk_workers
   if (bn % 32 != 0 || bn < 32 || bn > som::MAX_BN_2CTA)
     return fail(SOM_ERR_ARG, "pair tile width must be a multiple of 32 within the kernel's range");
   const int b_rows = bn / 2;                       // rows of the B tile held by one CTA
+  const int f16 = probs[0].f16, pmn = som::gemm_panel_mn(f16);
   bool need64 = nprob > 1;
-  for (int i = 0; i < nprob; ++i) need64 = need64 || probs[i].b_mn;
-  if (need64 && b_rows % 32 != 0) return fail(SOM_ERR_ARG, "pair tile width must be a multiple of 64 for MN-major B");
+  for (int i = 0; i < nprob; ++i) {
+    need64 = need64 || probs[i].b_mn;
+    if (probs[i].f16 != f16) return fail(SOM_ERR_ARG, "the GEMMs of one launch must share the operand precision");
+  }
+  if (need64 && b_rows % pmn != 0)
+    return fail(SOM_ERR_ARG, "pair tile width must be a multiple of two MN-major panels (64 tf32 / 128 fp16 columns)");
   som::PairMaps maps[2];
   som::GemmShape g[2];
   int64_t nwork = 0;
@@ -407,20 +428,20 @@ int launch_pair(int epi, const Problem* probs, int nprob, int bn, int sk_workers
     fill_shape(g[i], probs[i], 2, bn, kchunk, passes);
     // MN-major operands with panel-exact extents: one 3-D TMA operation per tile instead of one per panel
     const Problem& pr = probs[i];
-    if (g_tma3d.load() && pr.a_mn && pr.M % 32 == 0) {
-      if (int rc = make_tmap_mn3d(&maps[i].a_hi, pr.a_hi, pr.M, pr.Kred, pr.lda, som::BM / 32)) return rc;
-      if (int rc = make_tmap_mn3d(&maps[i].a_lo, pr.a_lo ? pr.a_lo : pr.a_hi, pr.M, pr.Kred, pr.lda, som::BM / 32)) return rc;
+    if (g_tma3d.load() && pr.a_mn && pr.M % pmn == 0) {
+      if (int rc = make_tmap_mn3d(&maps[i].a_hi, pr.a_hi, pr.M, pr.Kred, pr.lda, som::BM / pmn, f16)) return rc;
+      if (int rc = make_tmap_mn3d(&maps[i].a_lo, pr.a_lo ? pr.a_lo : pr.a_hi, pr.M, pr.Kred, pr.lda, som::BM / pmn, f16)) return rc;
       g[i].a_3d = 1;
     }
-    if (g_tma3d.load() && pr.b_mn && pr.N % 32 == 0 && b_rows % 32 == 0) {
-      if (int rc = make_tmap_mn3d(&maps[i].b_hi, pr.b_hi, pr.N, pr.Kred, pr.ldb, b_rows / 32)) return rc;
-      if (int rc = make_tmap_mn3d(&maps[i].b_lo, pr.b_lo ? pr.b_lo : pr.b_hi, pr.N, pr.Kred, pr.ldb, b_rows / 32)) return rc;
+    if (g_tma3d.load() && pr.b_mn && pr.N % pmn == 0 && b_rows % pmn == 0) {
+      if (int rc = make_tmap_mn3d(&maps[i].b_hi, pr.b_hi, pr.N, pr.Kred, pr.ldb, b_rows / pmn, f16)) return rc;
+      if (int rc = make_tmap_mn3d(&maps[i].b_lo, pr.b_lo ? pr.b_lo : pr.b_hi, pr.N, pr.Kred, pr.ldb, b_rows / pmn, f16)) return rc;
       g[i].b_3d = 1;
     }
     nwork += static_cast<int64_t>(g[i].tiles_m) * g[i].tiles_n;
   }
   if (nprob == 1) { maps[1] = maps[0]; g[1] = g[0]; }
-  const size_t b_tile = static_cast<size_t>(b_rows) * som::BK * 4;
+  const size_t b_tile = static_cast<size_t>(b_rows) * 128;      // bytes: b_rows x one 128-byte k span (either precision)
   const size_t stage = 2 * som::A_TILE_BYTES + 2 * b_tile;
   const size_t fixed = 1024 /*alignment slack*/ + som::BAR_REGION_BYTES;
   int nst = static_cast<int>((som::SMEM_LIMIT - fixed) / stage);
@@ -467,14 +488,14 @@ int effective_sms(int* sms, int sm_limit = 0) {
 int launch_gemm(int epi, const float* a_hi, const float* a_lo, int64_t lda, int a_mn, const float* b_hi,
                 const float* b_lo, int64_t ldb, int b_mn, int64_t M, int64_t N, int64_t Kred, int bn_req,
                 int kchunk_req, int passes, const som::EpiParams& e, float* ws, int64_t ws_floats, cudaStream_t st,
-                int sm_limit = 0) {
+                int sm_limit = 0, int f16 = 0) {
   int sms = 0;
   if (int rc = effective_sms(&sms, sm_limit)) return rc;
   if (passes != 1 && passes != 3) return fail(SOM_ERR_ARG, "passes must be 1 or 3");
   if (ws && (reinterpret_cast<uintptr_t>(ws) & 15) != 0) return fail(SOM_ERR_ARG, "workspace must be 16-byte aligned");
-  Problem p{a_hi, a_lo, lda, a_mn, b_hi, b_lo, ldb, b_mn, M, N, Kred, e};
+  Problem p{a_hi, a_lo, lda, a_mn, b_hi, b_lo, ldb, b_mn, M, N, Kred, e, f16};
   if (int rc = check_problem(p, passes)) return rc;
-  TileChoice tc = pick_tile(M, N, Kred, sms, b_mn, ws ? ws_floats : 0, bn_req);
+  TileChoice tc = pick_tile(M, N, Kred, sms, b_mn, ws ? ws_floats : 0, bn_req, f16);
   const int cg = tc.cg, bn = tc.bn;
   const int kchunk = kchunk_req > 0 ? kchunk_req : g_kchunk.load();
   if (cg == 2)
@@ -483,7 +504,9 @@ int launch_gemm(int epi, const float* a_hi, const float* a_lo, int64_t lda, int 
   if (bn % 16 != 0 || bn < 16 || bn > som::MAX_BN) return fail(SOM_ERR_ARG, "tile width must be a multiple of 16 within the kernel's range");
   som::GemmShape g;
   fill_shape(g, p, 1, bn, kchunk, passes);
-  const size_t b_tile = g.b_mn ? static_cast<size_t>((bn + 31) / 32) * som::PANEL_BYTES : static_cast<size_t>(bn) * som::BK * 4;
+  const int pmn = som::gemm_panel_mn(f16);
+  const size_t b_tile = g.b_mn ? static_cast<size_t>((bn + pmn - 1) / pmn) * (f16 ? som::PANEL_BYTES16 : som::PANEL_BYTES)
+                               : static_cast<size_t>(bn) * 128;
   const size_t stage = 2 * som::A_TILE_BYTES + 2 * b_tile;
   const size_t fixed = 1024 /*alignment slack*/ + som::BAR_REGION_BYTES;
   int nst = static_cast<int>((som::SMEM_LIMIT - fixed) / stage);
@@ -530,6 +553,51 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- 3xFP16 staging (SOM_PREC_FP16X3) -------------------------------------------------------------------------
+// A row v is staged as v * 2^e = hi + lo (+ residual) with hi, lo fp16 and 2^e the power of two that puts the row's
+// largest magnitude into [2^14, 2^15): fp16 has only 5 exponent bits, so the scale keeps hi AND (for every element
+// within 2^-17 of the row maximum) lo in the normal range - there the split carries 22 bits like the tf32 split; smaller
+// elements keep an absolute error of 2^-25, i.e. 2^-39 of the row maximum.  Scaling by a power of two is exact; the
+// GEMM epilogues multiply the accumulators by 2^-e of the row and the column.  aux of such a staging holds
+//   aux[0 .. rows)            |row|^2 or 1 / max(|row|, eps)   (as in the tf32 staging)
+//   aux[rows .. 2 rows)       2^-e
+//   aux[2 rows .. 3 rows)     2^e
+//   aux[3 rows .. 3 rows + 4) statistics of the forward this staging belongs to (latent staging only; see
+//                             bmu_decode_stat_kernel): [0] = bound on |R_unit| * 2^-e_b * 2^-g_k / inv_count
+constexpr int F16_TOP_EXP = 14;
+__device__ __forceinline__ float f16_row_scale(float amax) {
+  // floor(log2(amax)) from the exponent field; zero / denormal / non-finite rows keep scale 1
+  const int ex = static_cast<int>((__float_as_uint(amax) >> 23) & 0xffu);
+  if (ex == 0 || ex == 255) return 1.f;
+  int e = F16_TOP_EXP - (ex - 127);
+  e = e < -100 ? -100 : (e > 100 ? 100 : e);
+  return __uint_as_float(static_cast<uint32_t>(e + 127) << 23);
+}
+__device__ __forceinline__ void split_f16(float v, __half& h, __half& l) {
+  h = __float2half_rn(v);
+  l = __float2half_rn(v - __half2float(h));
+}
+__device__ __forceinline__ uint2 pack_half4(__half a, __half b, __half c, __half d) {
+  uint2 r;
+  r.x = static_cast<uint32_t>(__half_as_ushort(a)) | (static_cast<uint32_t>(__half_as_ushort(b)) << 16);
+  r.y = static_cast<uint32_t>(__half_as_ushort(c)) | (static_cast<uint32_t>(__half_as_ushort(d)) << 16);
+  return r;
+}
+// v (already normalised if the mode asks for it) * scale -> hi/lo halves at column i of the staged row
+__device__ __forceinline__ void store_split4_f16(__half* ph, __half* pl, int i, float4 v, float scale) {
+  __half h0, h1, h2, h3, l0, l1, l2, l3;
+  split_f16(v.x * scale, h0, l0); split_f16(v.y * scale, h1, l1);
+  split_f16(v.z * scale, h2, l2); split_f16(v.w * scale, h3, l3);
+  *reinterpret_cast<uint2*>(ph + i) = pack_half4(h0, h1, h2, h3);
+  *reinterpret_cast<uint2*>(pl + i) = pack_half4(l0, l1, l2, l3);
+}
+
 // GROUP threads cooperate on one row (GROUP = 32: warp per row, GROUP = 256: block per row).
 struct PrepSet {
   const float* src; long long rows; long long ld_src;
@@ -538,7 +606,7 @@ struct PrepSet {
 };
 
 // Stages up to two matrices of the same width in one launch (latents and prototypes of one forward).
-template <int GROUP>
+template <int GROUP, bool F16>
 __global__ void __launch_bounds__(256)
 prep_rows_kernel(const PrepSet sa, const PrepSet sb, long long blocks_a, int dim, int mode, long long ld_out) {
   som::pdl_wait();
@@ -554,6 +622,7 @@ prep_rows_kernel(const PrepSet sa, const PrepSet sb, long long blocks_a, int dim
   const long long rows = ps.rows, ld_src = ps.ld_src;
   const long long row = (static_cast<long long>(blockIdx.x) - (second ? blocks_a : 0)) * ROWS_PER_BLOCK + gi;
   __shared__ float red[8];
+  __shared__ float redm[8];
   const bool active = row < rows;
   const float* p = src + (active ? row : 0) * ld_src;
   const bool vec = (dim & 3) == 0 && (ld_src & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
@@ -562,7 +631,7 @@ prep_rows_kernel(const PrepSet sa, const PrepSet sb, long long blocks_a, int dim
   constexpr int PREP_CACHE = 8;
   const bool cached = vec && dim <= PREP_CACHE * GROUP * 4;
   float4 cache[PREP_CACHE];
-  float ss = 0.f;
+  float ss = 0.f, amax = 0.f;                    // amax: largest magnitude of the row (fp16 staging only)
   if (active) {
     if (cached) {
 #pragma unroll
@@ -572,23 +641,41 @@ prep_rows_kernel(const PrepSet sa, const PrepSet sb, long long blocks_a, int dim
         if (i < dim) cache[j] = __ldg(reinterpret_cast<const float4*>(p + i));
         const float4 v = cache[j];
         ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+        if constexpr (F16) amax = fmaxf(fmaxf(amax, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
       }
     } else if (vec) {
       for (int i = gt * 4; i < dim; i += GROUP * 4) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(p + i));
         ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+        if constexpr (F16) amax = fmaxf(fmaxf(amax, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
       }
     } else {
-      for (int i = gt; i < dim; i += GROUP) { const float v = __ldg(p + i); ss = fmaf(v, v, ss); }
+      for (int i = gt; i < dim; i += GROUP) {
+        const float v = __ldg(p + i);
+        ss = fmaf(v, v, ss);
+        if constexpr (F16) amax = fmaxf(amax, fabsf(v));
+      }
     }
   }
   ss = warp_sum(ss);
+  if constexpr (F16) amax = warp_max(amax);
   if constexpr (GROUP == 256) {
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = ss; redm[threadIdx.x >> 5] = amax; }
     __syncthreads();
     ss = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) ss += red[i];
+    if constexpr (F16) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) amax = fmaxf(amax, redm[i]);
+    }
+  }
+  if constexpr (F16) {
+    // the forward's statistics slot starts from zero (bmu_decode_stat_kernel raises it with atomicMax later in the stream)
+    if (blockIdx.x == 0 && threadIdx.x == 0 && sa.packed) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sa.aux[3 * sa.rows + i] = 0.f;
+    }
   }
   if (!active) return;
   if (ps.packed && gt == 0) ps.packed[row] = 0x7fffffffffffffffLL;
@@ -598,6 +685,41 @@ prep_rows_kernel(const PrepSet sa, const PrepSet sb, long long blocks_a, int dim
     if (gt == 0) aux[row] = 1.f / denom;
   } else if (gt == 0) {
     aux[row] = ss;
+  }
+  if constexpr (F16) {
+    // the normalised row's largest magnitude is amax / denom (division is monotone), its scale the power of two that
+    // lifts it into [2^14, 2^15)
+    const float scale = f16_row_scale(mode == 1 ? amax / denom : amax);
+    if (gt == 0) { aux[rows + row] = 1.f / scale; aux[2 * rows + row] = scale; }
+    __half* ph16 = reinterpret_cast<__half*>(hi) + row * ld_out;
+    __half* pl16 = reinterpret_cast<__half*>(lo) + row * ld_out;
+    const int dim_out16 = static_cast<int>(ld_out);
+    auto norm4 = [&](float4 v) {
+      if (mode == 1) { v.x = v.x / denom; v.y = v.y / denom; v.z = v.z / denom; v.w = v.w / denom; }
+      return v;
+    };
+    if (cached) {
+#pragma unroll
+      for (int j = 0; j < PREP_CACHE; ++j) {
+        const int i = (gt + j * GROUP) * 4;
+        if (i < dim_out16) store_split4_f16(ph16, pl16, i, i < dim ? norm4(cache[j]) : make_float4(0.f, 0.f, 0.f, 0.f), scale);
+      }
+    } else if (vec) {
+      for (int i = gt * 4; i < dim_out16; i += GROUP * 4)
+        store_split4_f16(ph16, pl16, i, i < dim ? norm4(__ldg(reinterpret_cast<const float4*>(p + i))) : make_float4(0.f, 0.f, 0.f, 0.f), scale);
+    } else {
+      for (int i = gt; i < dim_out16; i += GROUP) {
+        __half h = __float2half_rn(0.f), l = h;
+        if (i < dim) {
+          float v = __ldg(p + i);
+          if (mode == 1) v = v / denom;
+          split_f16(v * scale, h, l);
+        }
+        ph16[i] = h;
+        pl16[i] = l;
+      }
+    }
+    return;
   }
   float* ph = hi + row * ld_out;
   float* pl = lo + row * ld_out;
@@ -662,6 +784,65 @@ __global__ void bmu_decode_kernel(const long long* __restrict__ packed, long lon
     k ^= (k >> 31) & 0x7fffffff;
     min_key[i] = __int_as_float(k);
   }
+}
+
+// 3xFP16: BMU decode plus the statistic that lets the loss kernel place the staged backward operand
+//   R^[b,k] = R_unit[b,k] * 2^-e_b * 2^-g_k * S          (R_unit = inv_count * w / d, or inv_count * w for cosine)
+// into the fp16 range with ONE power of two S for the whole batch (the gradient GEMM over b cannot absorb a per-row
+// factor, the one over k no per-column factor; 2^-e_b and 2^-g_k cancel the scales of the staged latents / prototypes).
+// Since w <= 1 and d >= d_bmu(b):  R^ / (inv_count * S) <= 2^-e_b / d_bmu(b) * max_k 2^-g_k.  Every block takes the
+// maximum of the prototype scales itself (K floats from L2), the maximum over the rows is combined with atomicMax on the
+// bit pattern of the (positive) float - order independent, hence deterministic; the slot was zeroed by this forward's
+// staging kernel.  Rows whose BMU distance is zero (R is masked there) or below 2^-20 |x| (pure cancellation noise in
+// fp32) do not take part; the loss kernel saturates what would leave the fp16 range.
+__global__ void __launch_bounds__(256)
+bmu_decode_stat_kernel(const long long* __restrict__ packed, long long n, long long k_total, long long* __restrict__ bmu,
+                       float* __restrict__ min_key, float* __restrict__ x_aux, const float* __restrict__ w_aux,
+                       long long K, int dmode) {
+  som::pdl_wait();
+  som::pdl_launch_dependents();
+  __shared__ float redv[8], redw[8];
+  float mw = 0.f;
+  for (long long k = threadIdx.x; k < K; k += 256) mw = fmaxf(mw, __ldg(w_aux + K + k));
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  float val = 0.f;
+  if (i < n) {
+    const long long p = packed[i];
+    long long idx = p & 0xffffffffLL;
+    if (idx >= k_total) idx = 0;                    // NaN / all-inf rows: stay in bounds
+    if (bmu) bmu[i] = idx;
+    int kb = static_cast<int>(p >> 32);
+    kb ^= (kb >> 31) & 0x7fffffff;
+    const float key = __int_as_float(kb);          // squared BMU distance (euclidean) or BMU distance (cosine)
+    if (min_key) min_key[i] = key;
+    const float xs = x_aux[n + i];
+    if (dmode == 1) val = xs;
+    else if (key > 0.f && key >= 9.094947e-13f * x_aux[i]) val = xs * rsqrtf(key);     // d >= 2^-20 |x|
+    if (!(val < 3.0e38f)) val = 0.f;                // inf / NaN rows do not take part
+  }
+  val = warp_max(val);
+  mw = warp_max(mw);
+  if ((threadIdx.x & 31) == 0) { redv[threadIdx.x >> 5] = val; redw[threadIdx.x >> 5] = mw; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f, m = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { v = fmaxf(v, redv[j]); m = fmaxf(m, redw[j]); }
+    float t = v * m;
+    if (!(t < 3.0e38f)) t = 3.0e38f;
+    if (t > 0.f) atomicMax(reinterpret_cast<unsigned int*>(x_aux + 3 * n), __float_as_uint(t));
+  }
+}
+
+// S of the staged R (see bmu_decode_stat_kernel): the power of two that puts inv_count * stat into [2^13, 2^14).
+__device__ __forceinline__ float f16_r_scale(float stat, float inv_count) {
+  const float t = stat * inv_count;
+  if (!(t > 0.f) || !(t < 3.0e38f)) return 1.f;
+  int p;
+  frexpf(t, &p);                                    // t = m * 2^p, m in [0.5, 1)
+  int e = F16_TOP_EXP - p;
+  e = e < -120 ? -120 : (e > 120 ? 120 : e);
+  return __uint_as_float(static_cast<uint32_t>(e + 127) << 23);
 }
 
 // w = exp(-|p_k - p_bmu|^2 / (2 T^2)), written the way the reference evaluates it:
@@ -862,11 +1043,23 @@ loss_coeffs_kernel(const float* __restrict__ dist, long long ldd, const long lon
                    long long k_offset, const float* __restrict__ T_dev, float inv_count, int mode,
                    float* __restrict__ r_hi, float* __restrict__ r_lo, long long ldr,
                    float* __restrict__ row_part, int n_row_parts, float* __restrict__ col_part,
-                   float* __restrict__ partials, float* __restrict__ loss_out, int rows_per_block) {
+                   float* __restrict__ partials, float* __restrict__ loss_out, int rows_per_block,
+                   const float* __restrict__ x_aux, const float* __restrict__ w_aux) {
   som::pdl_wait();
   som::pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rh = warp >> 2, cs = warp & 3;
+  // 3xFP16 (x_aux != nullptr): R is staged as fp16 hi/lo of R * 2^-e_b * 2^-g_k * S (see bmu_decode_stat_kernel); r_hi / r_lo
+  // then are __half matrices with row pitch ldr halves.  1 / S goes behind the partial-sum tables for the GEMM epilogues.
+  const bool f16 = x_aux != nullptr;
+  float s_glob = 1.f;
+  if (f16) {
+    s_glob = f16_r_scale(__ldg(x_aux + 3 * B), inv_count);
+    if (r_hi && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+      row_part[B * n_row_parts] = 1.f / s_glob;
+      col_part[static_cast<long long>(gridDim.x) * K] = 1.f / s_glob;
+    }
+  }
   const int half_rows = rows_per_block >> 1;              // rows handled by each of the two warp rows (multiple of 4)
   const long long k0 = static_cast<long long>(blockIdx.y) * LC_COLS + cs * 128 + lane * 4;
   const long long b_base = static_cast<long long>(blockIdx.x) * rows_per_block + rh * half_rows;
@@ -874,6 +1067,11 @@ loss_coeffs_kernel(const float* __restrict__ dist, long long ldd, const long lon
   const bool want_r = r_hi != nullptr;
   const bool vec = (ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(dist) & 15) == 0 &&
                    (!want_r || ((ldr & 3) == 0 && ((reinterpret_cast<uintptr_t>(r_hi) | reinterpret_cast<uintptr_t>(r_lo)) & 15) == 0));
+  float wsc[4] = {0.f, 0.f, 0.f, 0.f};                     // fp16: 2^-g_k * S of this lane's columns
+  if (f16) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) if (k0 + i < K) wsc[i] = __ldg(w_aux + K + k0 + i) * s_glob;
+  }
   __shared__ float lred[8];
   __shared__ float csum[LC_COLS];
   __shared__ float tab[SQUARE ? LC_MAX_TAB : 1];
@@ -962,6 +1160,7 @@ loss_coeffs_kernel(const float* __restrict__ dist, long long ldd, const long lon
       const int rb = __shfl_sync(0xffffffffu, rbv, r), cb = __shfl_sync(0xffffffffu, cbv, r);
       if (b >= B) break;                                   // warp-uniform
       const float (&d)[4] = dc[r];
+      const float xsb = f16 ? __ldg(x_aux + B + b) : 1.f;
       float h[4], l[4], rowterm = 0.f;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -981,14 +1180,31 @@ loss_coeffs_kernel(const float* __restrict__ dist, long long ldd, const long lon
               rv = g;
               term = g * (1.f - d[i]);                     // g * (x^ . w^): projection coefficient of normalize backward
             }
-            h[i] = tf32_rna(rv);
-            l[i] = tf32_rna(rv - h[i]);
+            if (f16) {
+              h[i] = fminf((rv * xsb) * wsc[i], 60000.f);   // scaled value; split below
+            } else {
+              h[i] = tf32_rna(rv);
+              l[i] = tf32_rna(rv - h[i]);
+            }
             colsum[i] += term;
             rowterm += term;
           }
         }
       }
-      if (want_r) {
+      if (want_r && f16) {
+        __half* hp16 = reinterpret_cast<__half*>(r_hi) + b * ldr + k0;
+        __half* lp16 = reinterpret_cast<__half*>(r_lo) + b * ldr + k0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (ok[i]) {
+            __half hh, ll;
+            split_f16(h[i], hh, ll);
+            hp16[i] = hh; lp16[i] = ll;
+          }
+        }
+        rowterm = warp_sum(rowterm);
+        if (lane == 0 && slab < n_row_parts) row_part[b * n_row_parts + slab] = rowterm;
+      } else if (want_r) {
         if (ok[0]) {
           if (vec) {
             *reinterpret_cast<float4*>(r_hi + b * ldr + k0) = make_float4(h[0], h[1], h[2], h[3]);
@@ -1049,16 +1265,26 @@ loss_coeffs_kernel(const float* __restrict__ dist, long long ldd, const long lon
 // bound at 3.9 TB/s on a 4096 x 16384 chunk) on per-element predicates, 64-bit index arithmetic and two table lookups
 // per element; here the row factor of the weight is looked up once per lane and row, inv_count is folded into it,
 // pointers advance by increments and nothing is predicated per element.
-template <int MODE>
+template <int MODE, bool F16>
 __global__ void __launch_bounds__(256)
 loss_coeffs_fast_kernel(const float* __restrict__ dist, long long ldd, const long long* __restrict__ bmu,
                         int grid_rows, int grid_cols, long long B, long long K, long long k_offset,
                         const float* __restrict__ T_dev, float inv_count,
                         float* __restrict__ r_hi, float* __restrict__ r_lo, long long ldr,
                         float* __restrict__ row_part, int n_row_parts, float* __restrict__ col_part,
-                        float* __restrict__ partials, float* __restrict__ loss_out, int rows_per_block) {
+                        float* __restrict__ partials, float* __restrict__ loss_out, int rows_per_block,
+                        const float* __restrict__ x_aux, const float* __restrict__ w_aux) {
   som::pdl_wait();
   som::pdl_launch_dependents();
+  // F16: R staged as fp16 hi/lo of R * 2^-e_b * 2^-g_k * S (see loss_coeffs_kernel / bmu_decode_stat_kernel)
+  float s_glob = 1.f;
+  if constexpr (F16) {
+    s_glob = f16_r_scale(__ldg(x_aux + 3 * B), inv_count);
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+      row_part[B * n_row_parts] = 1.f / s_glob;
+      col_part[static_cast<long long>(gridDim.x) * K] = 1.f / s_glob;
+    }
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rh = warp >> 2, cs = warp & 3;
   const int half_rows = rows_per_block >> 1;
@@ -1091,6 +1317,15 @@ loss_coeffs_fast_kernel(const float* __restrict__ dist, long long ldd, const lon
   const float* dp = dist + b_base * ldd + k0;
   float* hp = r_hi + b_base * ldr + k0;
   float* lp = r_lo + b_base * ldr + k0;
+  __half* hp16 = reinterpret_cast<__half*>(r_hi) + b_base * ldr + k0;      // F16: half matrices, pitch ldr halves
+  __half* lp16 = reinterpret_cast<__half*>(r_lo) + b_base * ldr + k0;
+  float4 csc = make_float4(0.f, 0.f, 0.f, 0.f);                            // F16: 2^-g_k * S of this lane's 4 columns
+  if constexpr (F16) {
+    if (col_ok) {
+      csc = __ldg(reinterpret_cast<const float4*>(w_aux + K + k0));
+      csc.x *= s_glob; csc.y *= s_glob; csc.z *= s_glob; csc.w *= s_glob;
+    }
+  }
   float* rp = row_part + b_base * n_row_parts + slab;
   const bool slab_ok = slab < n_row_parts;
   auto load4 = [&](int r, float4& v) {
@@ -1103,10 +1338,12 @@ loss_coeffs_fast_kernel(const float* __restrict__ dist, long long ldd, const lon
   auto process = [&](const float4 (&dg)[4], int r4) {
     // BMU cell of these 4 rows: lane r loads row r, one shuffle per row broadcasts (row << 16 | column)
     int cell = 0;
+    float xsl = 0.f;                                       // F16: 2^-e of the row this lane fetched
     if (lane < 4 && r4 + lane < nrows) {
       const unsigned ub = static_cast<unsigned>(bmu[b_base + r4 + lane]);
       const unsigned rb = ub / static_cast<unsigned>(grid_cols);
       cell = static_cast<int>((rb << 16) | (ub - rb * static_cast<unsigned>(grid_cols)));
+      if constexpr (F16) xsl = __ldg(x_aux + B + b_base + r4 + lane);
     }
     float t[4];
 #pragma unroll
@@ -1131,17 +1368,26 @@ loss_coeffs_fast_kernel(const float* __restrict__ dist, long long ldd, const lon
         rv = make_float4(w0, w1, w2, w3);
         term = make_float4(w0 * (1.f - d.x), w1 * (1.f - d.y), w2 * (1.f - d.z), w3 * (1.f - d.w));
       }
-      float4 h, l;
-      h.x = tf32_rna_finite(rv.x); h.y = tf32_rna_finite(rv.y); h.z = tf32_rna_finite(rv.z); h.w = tf32_rna_finite(rv.w);
-      l.x = tf32_rna_finite(rv.x - h.x); l.y = tf32_rna_finite(rv.y - h.y);
-      l.z = tf32_rna_finite(rv.z - h.z); l.w = tf32_rna_finite(rv.w - h.w);
-      if (col_ok && row_ok) {
-        *reinterpret_cast<float4*>(hp) = h;
-        *reinterpret_cast<float4*>(lp) = l;
+      if constexpr (F16) {
+        const float xsb = __shfl_sync(0xffffffffu, xsl, r);
+        float4 q;
+        q.x = fminf((rv.x * xsb) * csc.x, 60000.f); q.y = fminf((rv.y * xsb) * csc.y, 60000.f);
+        q.z = fminf((rv.z * xsb) * csc.z, 60000.f); q.w = fminf((rv.w * xsb) * csc.w, 60000.f);
+        if (col_ok && row_ok) store_split4_f16(hp16, lp16, 0, q, 1.f);
+        hp16 += ldr; lp16 += ldr;
+      } else {
+        float4 h, l;
+        h.x = tf32_rna_finite(rv.x); h.y = tf32_rna_finite(rv.y); h.z = tf32_rna_finite(rv.z); h.w = tf32_rna_finite(rv.w);
+        l.x = tf32_rna_finite(rv.x - h.x); l.y = tf32_rna_finite(rv.y - h.y);
+        l.z = tf32_rna_finite(rv.z - h.z); l.w = tf32_rna_finite(rv.w - h.w);
+        if (col_ok && row_ok) {
+          *reinterpret_cast<float4*>(hp) = h;
+          *reinterpret_cast<float4*>(lp) = l;
+        }
+        hp += ldr; lp += ldr;
       }
       colsum0 += term.x; colsum1 += term.y; colsum2 += term.z; colsum3 += term.w;
       t[r] = col_ok ? (term.x + term.y) + (term.z + term.w) : 0.f;
-      hp += ldr; lp += ldr;
     }
     // the four row sums of the group in one transposed butterfly (6 shuffles instead of 20; a fixed pattern, so the
     // result is the same in every run): after the 16- and 8-steps a lane carries ONE of the rows, selected by its bits
@@ -1236,7 +1482,7 @@ inline int loss_rows_per_block(int64_t B, int64_t K, int sms) {
 struct AdamHyper { double beta1, beta2, eps, weight_decay; };   // doubles, like torch's Python scalars
 
 // GROUP threads cooperate on one row (GROUP = 32: warp per row for short rows, GROUP = 256: block per row).
-template <int GROUP>
+template <int GROUP, bool F16>
 __global__ void __launch_bounds__(256, 2)
 adamw_stage_kernel(float* __restrict__ W, long long ldw, const float* __restrict__ dW, long long lddw,
                    float* __restrict__ m, float* __restrict__ v, long long ldm, long long rows, int dim,
@@ -1276,7 +1522,7 @@ adamw_stage_kernel(float* __restrict__ W, long long ldw, const float* __restrict
   constexpr int CACHE = 8;
   const bool cached = vec && dim <= CACHE * GROUP * 4;      // the new row waits in registers for its norm
   float4 cache[CACHE];
-  float ss = 0.f;
+  float ss = 0.f, amax = 0.f;                                // amax: largest magnitude of the new row (fp16 staging)
   if (active) {
     if (cached) {
       // four row segments at a time: all their loads first (4 arrays x 4 x 16 bytes in flight per thread), then the
@@ -1307,6 +1553,7 @@ adamw_stage_kernel(float* __restrict__ W, long long ldw, const float* __restrict
             *reinterpret_cast<float4*>(mrow + i) = mm;
             *reinterpret_cast<float4*>(vrow + i) = vv;
             ss = fmaf(w.x, w.x, ss); ss = fmaf(w.y, w.y, ss); ss = fmaf(w.z, w.z, ss); ss = fmaf(w.w, w.w, ss);
+            if constexpr (F16) amax = fmaxf(fmaxf(amax, fmaxf(fabsf(w.x), fabsf(w.y))), fmaxf(fabsf(w.z), fabsf(w.w)));
             cache[j0 + jj] = w;
           }
         }
@@ -1323,6 +1570,7 @@ adamw_stage_kernel(float* __restrict__ W, long long ldw, const float* __restrict
         *reinterpret_cast<float4*>(mrow + i) = mm;
         *reinterpret_cast<float4*>(vrow + i) = vv;
         ss = fmaf(w.x, w.x, ss); ss = fmaf(w.y, w.y, ss); ss = fmaf(w.z, w.z, ss); ss = fmaf(w.w, w.w, ss);
+        if constexpr (F16) amax = fmaxf(fmaxf(amax, fmaxf(fabsf(w.x), fabsf(w.y))), fmaxf(fabsf(w.z), fabsf(w.w)));
       }
     } else {
       for (int i = gt; i < dim; i += GROUP) {
@@ -1330,18 +1578,25 @@ adamw_stage_kernel(float* __restrict__ W, long long ldw, const float* __restrict
         const float w = update(wrow[i], __ldg(grow + i), mm, vv);
         wrow[i] = w; mrow[i] = mm; vrow[i] = vv;
         ss = fmaf(w, w, ss);
+        if constexpr (F16) amax = fmaxf(amax, fabsf(w));
       }
     }
   }
   if (!hi) return;                                           // optimizer step only (no staging requested): uniform
   ss = warp_sum(ss);
+  if constexpr (F16) amax = warp_max(amax);
   if constexpr (GROUP == 256) {
     __shared__ float red[8];
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __shared__ float redm[8];
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = ss; redm[threadIdx.x >> 5] = amax; }
     __syncthreads();
     ss = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) ss += red[i];
+    if constexpr (F16) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) amax = fmaxf(amax, redm[i]);
+    }
   }
   if (!active) return;
   float denom = 1.f;
@@ -1350,6 +1605,40 @@ adamw_stage_kernel(float* __restrict__ W, long long ldw, const float* __restrict
     if (gt == 0) aux[row] = 1.f / denom;
   } else if (gt == 0) {
     aux[row] = ss;
+  }
+  if constexpr (F16) {
+    // the row-scaled fp16 split of the NEW prototypes, exactly what prep_rows_kernel<GROUP, true> would stage
+    const float scale = f16_row_scale(mode == 1 ? amax / denom : amax);
+    if (gt == 0) { aux[rows + row] = 1.f / scale; aux[2 * rows + row] = scale; }
+    __half* ph16 = reinterpret_cast<__half*>(hi) + row * ld_out;
+    __half* pl16 = reinterpret_cast<__half*>(lo) + row * ld_out;
+    const int dim_out16 = static_cast<int>(ld_out);
+    auto norm4 = [&](float4 w) {
+      if (mode == 1) { w.x = w.x / denom; w.y = w.y / denom; w.z = w.z / denom; w.w = w.w / denom; }
+      return w;
+    };
+    if (cached) {
+#pragma unroll
+      for (int j = 0; j < CACHE; ++j) {
+        const int i = (gt + j * GROUP) * 4;
+        if (i < dim_out16) store_split4_f16(ph16, pl16, i, i < dim ? norm4(cache[j]) : make_float4(0.f, 0.f, 0.f, 0.f), scale);
+      }
+    } else if (vec) {
+      for (int i = gt * 4; i < dim_out16; i += GROUP * 4)
+        store_split4_f16(ph16, pl16, i, i < dim ? norm4(*reinterpret_cast<const float4*>(wrow + i)) : make_float4(0.f, 0.f, 0.f, 0.f), scale);
+    } else {
+      for (int i = gt; i < dim_out16; i += GROUP) {
+        __half h = __float2half_rn(0.f), l = h;
+        if (i < dim) {
+          float w = wrow[i];
+          if (mode == 1) w = w / denom;
+          split_f16(w * scale, h, l);
+        }
+        ph16[i] = h;
+        pl16[i] = l;
+      }
+    }
+    return;
   }
   float* ph = hi + row * ld_out;
   float* pl = lo + row * ld_out;
@@ -1470,14 +1759,22 @@ nvls_allreduce_mean_kernel(float* mc, unsigned int* const* flag_ptrs, long long 
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// mode: distance mode (bit 0) | SOM_PREC_FP16X3
 int launch_prep(const PrepSet& a, const PrepSet& b, int64_t dim, int mode, int64_t ld_out, cudaStream_t st) {
   const int per_block = dim <= 1024 ? 8 : 1;
   const long long blocks_a = (a.rows + per_block - 1) / per_block;
   const long long blocks_b = b.src ? (b.rows + per_block - 1) / per_block : 0;
   if (blocks_a + blocks_b > 0x7fffffffLL) return fail(SOM_ERR_ARG, "too many rows to stage in one launch");
   const unsigned grid = static_cast<unsigned>(blocks_a + blocks_b);
-  if (dim <= 1024) SOM_CUDA(launch_kernel(prep_rows_kernel<32>, dim3(grid), dim3(256), 0, st, a, b, blocks_a, static_cast<int>(dim), mode, ld_out));
-  else             SOM_CUDA(launch_kernel(prep_rows_kernel<256>, dim3(grid), dim3(256), 0, st, a, b, blocks_a, static_cast<int>(dim), mode, ld_out));
+  const int dmode = mode & 1;
+  const long long ld = ld_out;
+  if (mode & SOM_PREC_FP16X3) {
+    if (dim <= 1024) SOM_CUDA(launch_kernel(prep_rows_kernel<32, true>, dim3(grid), dim3(256), 0, st, a, b, blocks_a, static_cast<int>(dim), dmode, ld));
+    else             SOM_CUDA(launch_kernel(prep_rows_kernel<256, true>, dim3(grid), dim3(256), 0, st, a, b, blocks_a, static_cast<int>(dim), dmode, ld));
+  } else {
+    if (dim <= 1024) SOM_CUDA(launch_kernel(prep_rows_kernel<32, false>, dim3(grid), dim3(256), 0, st, a, b, blocks_a, static_cast<int>(dim), dmode, ld));
+    else             SOM_CUDA(launch_kernel(prep_rows_kernel<256, false>, dim3(grid), dim3(256), 0, st, a, b, blocks_a, static_cast<int>(dim), dmode, ld));
+  }
   g_launches.fetch_add(1);
   return SOM_OK;
 }
@@ -1489,7 +1786,7 @@ int launch_prep(const PrepSet& a, const PrepSet& b, int64_t dim, int mode, int64
 // ------------------------------------------------------------------------------------------------
 extern "C" {
 
-int som_b200_abi_version(void) { return 6; }
+int som_b200_abi_version(void) { return 7; }
 const char* som_last_error(void) { return g_last_error.c_str(); }
 int64_t som_launch_count(void) { return g_launches.load(); }
 void som_launch_count_reset(void) { g_launches.store(0); }
@@ -1521,9 +1818,9 @@ int som_prep_rows(const float* src, int64_t rows, int64_t dim, int64_t ld_src, i
   if (!src || !hi || !lo || !aux) return fail(SOM_ERR_ARG, "som_prep_rows: null pointer");
   if (rows <= 0 || dim <= 0 || dim > (1ll << 30) || ld_src < dim || ld_out < dim)
     return fail(SOM_ERR_ARG, "som_prep_rows: bad shape");
-  if ((ld_out & 3) != 0 || ((reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 15) != 0)
-    return fail(SOM_ERR_ARG, "som_prep_rows: hi/lo must be 16-byte aligned with ld_out % 4 == 0");
-  if (mode != SOM_MODE_EUCLIDEAN && mode != SOM_MODE_COSINE) return fail(SOM_ERR_ARG, "som_prep_rows: bad mode");
+  if (!mode_ok(mode)) return fail(SOM_ERR_ARG, "som_prep_rows: bad mode");
+  if ((ld_out & (mode_f16(mode) ? 7 : 3)) != 0 || ((reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 15) != 0)
+    return fail(SOM_ERR_ARG, "som_prep_rows: hi/lo must be 16-byte aligned with a row pitch that is a multiple of 16 bytes");
   PrepSet a{src, rows, ld_src, hi, lo, aux, nullptr}, none{};
   return launch_prep(a, none, dim, mode, ld_out, as_stream(stream));
 }
@@ -1543,15 +1840,17 @@ int som_fwd_distances(const float* x_hi, const float* x_lo, int64_t ldx, const f
                       int64_t idx_offset, float* dist, int64_t ldd, long long* packed, float* ws, int64_t ws_floats,
                       void* stream) {
   if (!packed) return fail(SOM_ERR_ARG, "som_fwd_distances: packed must not be null");
-  if (mode != SOM_MODE_EUCLIDEAN && mode != SOM_MODE_COSINE) return fail(SOM_ERR_ARG, "som_fwd_distances: bad mode");
-  if (mode == SOM_MODE_EUCLIDEAN && (!x_aux || !w_aux)) return fail(SOM_ERR_ARG, "som_fwd_distances: norms required");
+  if (!mode_ok(mode)) return fail(SOM_ERR_ARG, "som_fwd_distances: bad mode");
+  const int f16 = mode_f16(mode), dmode = mode & 1;
+  if ((dmode == SOM_MODE_EUCLIDEAN || f16) && (!x_aux || !w_aux)) return fail(SOM_ERR_ARG, "som_fwd_distances: aux vectors required");
   if (dist && ldd < K) return fail(SOM_ERR_ARG, "som_fwd_distances: ldd < K");
   if (idx_offset < 0 || idx_offset + K > 0x7fffffffLL) return fail(SOM_ERR_ARG, "som_fwd_distances: index range");
   som::EpiParams e{};
   e.row_aux = x_aux; e.col_aux = w_aux; e.dist = dist; e.ldd = ldd; e.packed = packed;
-  e.idx_offset = static_cast<int>(idx_offset); e.mode = mode;
+  e.idx_offset = static_cast<int>(idx_offset); e.mode = dmode;
+  if (f16) { e.row_scale = x_aux + B; e.col_scale = w_aux + K; }        // the 2^-e of the staged rows
   return launch_gemm(som::EPI_DIST, x_hi, x_lo, ldx, 0, w_hi, w_lo, ldw, 0, B, K, D, 0, 0, 3, e, ws, ws_floats,
-                     as_stream(stream));
+                     as_stream(stream), 0, f16);
 }
 
 int som_bmu_decode(const long long* packed, int64_t B, int64_t K_total, int64_t* bmu, float* min_key, void* stream) {
@@ -1561,6 +1860,19 @@ int som_bmu_decode(const long long* packed, int64_t B, int64_t K_total, int64_t*
   SOM_CUDA(launch_kernel(bmu_decode_kernel, dim3(static_cast<unsigned>((B + 255) / 256)), dim3(256), 0, as_stream(stream),
                          packed, static_cast<long long>(B), static_cast<long long>(K_total),
                          reinterpret_cast<long long*>(bmu), min_key));
+  g_launches.fetch_add(1);
+  return SOM_OK;
+}
+
+int som_bmu_decode_scaled(const long long* packed, int64_t B, int64_t K_total, int64_t* bmu, float* min_key,
+                          float* x_aux, const float* w_aux, int64_t K, int mode, void* stream) {
+  DeviceInfo di;
+  if (int rc = device_info(di)) return rc;
+  if (!packed || B <= 0 || K_total <= 0 || K <= 0 || !x_aux || !w_aux || !mode_ok(mode) || !mode_f16(mode))
+    return fail(SOM_ERR_ARG, "som_bmu_decode_scaled: bad argument (fp16 stagings of this forward required)");
+  SOM_CUDA(launch_kernel(bmu_decode_stat_kernel, dim3(static_cast<unsigned>((B + 255) / 256)), dim3(256), 0, as_stream(stream),
+                         packed, static_cast<long long>(B), static_cast<long long>(K_total),
+                         reinterpret_cast<long long*>(bmu), min_key, x_aux, w_aux, static_cast<long long>(K), mode & 1));
   g_launches.fetch_add(1);
   return SOM_OK;
 }
@@ -1665,14 +1977,16 @@ int som_forward(const float* x, int64_t ldx, const float* W, int64_t ldw, int64_
   if (stage_w && !W) return fail(SOM_ERR_ARG, "som_forward: prototypes required when stage_w is set");
   if (B <= 0 || K <= 0 || D <= 0 || D > (1ll << 30) || ldx < D || (stage_w && ldw < D) || ld_stage < D)
     return fail(SOM_ERR_ARG, "som_forward: bad shape");
-  if ((ld_stage & 3) != 0) return fail(SOM_ERR_ARG, "som_forward: ld_stage must be a multiple of 4");
-  if (mode != SOM_MODE_EUCLIDEAN && mode != SOM_MODE_COSINE) return fail(SOM_ERR_ARG, "som_forward: bad mode");
+  if (!mode_ok(mode)) return fail(SOM_ERR_ARG, "som_forward: bad mode");
+  if ((ld_stage & (mode_f16(mode) ? 7 : 3)) != 0) return fail(SOM_ERR_ARG, "som_forward: the staging row pitch must be a multiple of 16 bytes");
   PrepSet a{x, B, ldx, x_hi, x_lo, x_aux, packed}, b{};
   if (stage_w) b = PrepSet{W, K, ldw, w_hi, w_lo, w_aux, nullptr};
   if (int rc = launch_prep(a, b, D, mode, ld_stage, as_stream(stream))) return rc;
   if (int rc = som_fwd_distances(x_hi, x_lo, ld_stage, x_aux, w_hi, w_lo, ld_stage, w_aux, B, K, D, mode, idx_offset,
                                  dist, ldd, packed, ws, ws_floats, stream))
     return rc;
+  if (bmu && mode_f16(mode))
+    return som_bmu_decode_scaled(packed, B, K_total > 0 ? K_total : K, bmu, nullptr, x_aux, w_aux, K, mode, stream);
   if (bmu) return som_bmu_decode(packed, B, K_total > 0 ? K_total : K, bmu, nullptr, stream);
   return SOM_OK;
 }
@@ -1690,13 +2004,20 @@ int som_loss_fused_parts(int64_t B, int64_t K, int64_t* n_row_parts, int64_t* n_
 int som_loss_fused(const float* dist, int64_t ldd, const int64_t* bmu, const float* grid_pos, int grid_rows,
                    int grid_cols, int64_t B, int64_t K, int64_t k_offset, const float* T_dev, float inv_count, int mode,
                    float* r_hi, float* r_lo, int64_t ldr, float* row_part, float* col_part, float* scratch,
-                   float* loss_out, void* stream) {
+                   float* loss_out, const float* x_aux, const float* w_aux, void* stream) {
   DeviceInfo di;
   if (int rc = device_info(di)) return rc;
   if (!dist || !bmu || !grid_pos || !T_dev || !scratch || !loss_out || B <= 0 || K <= 0 || ldd < K)
     return fail(SOM_ERR_ARG, "som_loss_fused: bad argument");
-  if (mode != SOM_MODE_EUCLIDEAN && mode != SOM_MODE_COSINE) return fail(SOM_ERR_ARG, "som_loss_fused: bad mode");
+  if (!mode_ok(mode)) return fail(SOM_ERR_ARG, "som_loss_fused: bad mode");
+  const int f16 = (mode_f16(mode) && r_hi) ? 1 : 0;     // the precision only concerns the backward staging
+  const int dmode = mode & 1;
   if (r_hi && (!r_lo || !row_part || !col_part || ldr < K)) return fail(SOM_ERR_ARG, "som_loss_fused: bad backward staging");
+  if (f16 && (!x_aux || !w_aux || (ldr & 7) != 0 ||
+              ((reinterpret_cast<uintptr_t>(r_hi) | reinterpret_cast<uintptr_t>(r_lo)) & 15) != 0))
+    return fail(SOM_ERR_ARG, "som_loss_fused: fp16 staging needs the aux vectors of both stagings, ldr % 8 == 0 and aligned R");
+  const float* xa = f16 ? x_aux : nullptr;
+  const float* wa = f16 ? w_aux : nullptr;
   // grid_rows / grid_cols > 0: the caller vouches that grid_pos is the canonical square grid (cell k at (k / cols, k % cols))
   const bool square = grid_rows > 0 && grid_cols > 0 && grid_rows <= LC_MAX_TAB && grid_cols <= LC_MAX_TAB;
   const int rpb = loss_rows_per_block(B, K, di.sms);
@@ -1707,28 +2028,32 @@ int som_loss_fused(const float* dist, int64_t ldd, const int64_t* bmu, const flo
   const bool fast = square && r_hi && g_loss_fast.load() && (K & 3) == 0 && (grid_cols & 3) == 0 && (k_offset & 3) == 0 &&
                     (ldd & 3) == 0 && (ldr & 3) == 0 && grid_rows < 65536 && grid_cols < 65536 &&
                     ((reinterpret_cast<uintptr_t>(dist) | reinterpret_cast<uintptr_t>(r_hi) | reinterpret_cast<uintptr_t>(r_lo) |
-                      reinterpret_cast<uintptr_t>(col_part)) & 15) == 0;
+                      reinterpret_cast<uintptr_t>(col_part)) & 15) == 0 &&
+                    (!f16 || (reinterpret_cast<uintptr_t>(w_aux + K) & 15) == 0);
+  auto launch_fast = [&](auto kernel) {
+    return launch_kernel(kernel, grid, dim3(256), 0, as_stream(stream), dist, static_cast<long long>(ldd), bmu_ll, grid_rows,
+                         grid_cols, static_cast<long long>(B), static_cast<long long>(K), static_cast<long long>(k_offset),
+                         T_dev, inv_count, r_hi, r_lo, static_cast<long long>(ldr), row_part, n_row_parts, col_part, scratch,
+                         loss_out, rpb, xa, wa);
+  };
   if (fast) {
-    if (mode == SOM_MODE_EUCLIDEAN)
-      SOM_CUDA(launch_kernel(loss_coeffs_fast_kernel<0>, grid, dim3(256), 0, as_stream(stream), dist, static_cast<long long>(ldd),
-                             bmu_ll, grid_rows, grid_cols, static_cast<long long>(B), static_cast<long long>(K),
-                             static_cast<long long>(k_offset), T_dev, inv_count, r_hi, r_lo, static_cast<long long>(ldr),
-                             row_part, n_row_parts, col_part, scratch, loss_out, rpb));
-    else
-      SOM_CUDA(launch_kernel(loss_coeffs_fast_kernel<1>, grid, dim3(256), 0, as_stream(stream), dist, static_cast<long long>(ldd),
-                             bmu_ll, grid_rows, grid_cols, static_cast<long long>(B), static_cast<long long>(K),
-                             static_cast<long long>(k_offset), T_dev, inv_count, r_hi, r_lo, static_cast<long long>(ldr),
-                             row_part, n_row_parts, col_part, scratch, loss_out, rpb));
+    if (dmode == SOM_MODE_EUCLIDEAN) {
+      if (f16) SOM_CUDA(launch_fast(loss_coeffs_fast_kernel<0, true>));
+      else     SOM_CUDA(launch_fast(loss_coeffs_fast_kernel<0, false>));
+    } else {
+      if (f16) SOM_CUDA(launch_fast(loss_coeffs_fast_kernel<1, true>));
+      else     SOM_CUDA(launch_fast(loss_coeffs_fast_kernel<1, false>));
+    }
   } else if (square)
     SOM_CUDA(launch_kernel(loss_coeffs_kernel<true>, grid, dim3(256), 0, as_stream(stream), dist, static_cast<long long>(ldd),
                            bmu_ll, grid_pos, grid_rows, grid_cols, static_cast<long long>(B), static_cast<long long>(K),
-                           static_cast<long long>(k_offset), T_dev, inv_count, mode, r_hi, r_lo, static_cast<long long>(ldr),
-                           row_part, n_row_parts, col_part, scratch, loss_out, rpb));
+                           static_cast<long long>(k_offset), T_dev, inv_count, dmode, r_hi, r_lo, static_cast<long long>(ldr),
+                           row_part, n_row_parts, col_part, scratch, loss_out, rpb, xa, wa));
   else
     SOM_CUDA(launch_kernel(loss_coeffs_kernel<false>, grid, dim3(256), 0, as_stream(stream), dist, static_cast<long long>(ldd),
                            bmu_ll, grid_pos, 0, 0, static_cast<long long>(B), static_cast<long long>(K),
-                           static_cast<long long>(k_offset), T_dev, inv_count, mode, r_hi, r_lo, static_cast<long long>(ldr),
-                           row_part, n_row_parts, col_part, scratch, loss_out, rpb));
+                           static_cast<long long>(k_offset), T_dev, inv_count, dmode, r_hi, r_lo, static_cast<long long>(ldr),
+                           row_part, n_row_parts, col_part, scratch, loss_out, rpb, xa, wa));
   g_launches.fetch_add(1);
   return SOM_OK;
 }
@@ -1743,13 +2068,16 @@ int som_backward_dw(const float* r_hi, const float* r_lo, int64_t ldr, const flo
                     int64_t lddw, int accumulate, int sm_limit, float* ws, int64_t ws_floats, void* stream) {
   if (!W || !col_part || n_col_parts <= 0 || !g_dev || !dW || ldw < D || lddw < D)
     return fail(SOM_ERR_ARG, "som_backward_dw: bad argument");
-  if (mode == SOM_MODE_COSINE && !w_aux) return fail(SOM_ERR_ARG, "som_backward_dw: cosine needs the reciprocal norms");
+  if (!mode_ok(mode)) return fail(SOM_ERR_ARG, "som_backward_dw: bad mode");
+  const int f16 = mode_f16(mode), dmode = mode & 1;
+  if ((dmode == SOM_MODE_COSINE || f16) && !w_aux) return fail(SOM_ERR_ARG, "som_backward_dw: the prototype staging's aux vector is required");
   som::EpiParams e{};
   e.sum = col_part; e.sum_n = static_cast<int>(n_col_parts); e.sum_ld_m = 1; e.sum_ld_j = K;
-  e.aux = w_aux; e.g_dev = g_dev; e.mode = mode; e.accumulate = accumulate;
+  e.aux = w_aux; e.g_dev = g_dev; e.mode = dmode; e.accumulate = accumulate;
   e.src = W; e.lds = ldw; e.out = dW; e.ldo = lddw;
+  if (f16) { e.grad_scale = w_aux + 2 * K; e.grad_inv_s = col_part + n_col_parts * K; }   // 2^g_k, 1 / S (loss kernel)
   return launch_gemm(som::EPI_GRAD, r_hi, r_lo, ldr, 1, x_hi, x_lo, ld_stage, 1, K, D, B, 0, 0, 3, e, ws, ws_floats,
-                     as_stream(stream), sm_limit);
+                     as_stream(stream), sm_limit, f16);
 }
 
 int som_backward_dx(const float* r_hi, const float* r_lo, int64_t ldr, const float* w_hi, const float* w_lo,
@@ -1758,13 +2086,16 @@ int som_backward_dx(const float* r_hi, const float* r_lo, int64_t ldr, const flo
                     int64_t lddx, int accumulate, int sm_limit, float* ws, int64_t ws_floats, void* stream) {
   if (!x || !row_part || n_row_parts <= 0 || !g_dev || !dx || ldx < D || lddx < D)
     return fail(SOM_ERR_ARG, "som_backward_dx: bad argument");
-  if (mode == SOM_MODE_COSINE && !x_aux) return fail(SOM_ERR_ARG, "som_backward_dx: cosine needs the reciprocal norms");
+  if (!mode_ok(mode)) return fail(SOM_ERR_ARG, "som_backward_dx: bad mode");
+  const int f16 = mode_f16(mode), dmode = mode & 1;
+  if ((dmode == SOM_MODE_COSINE || f16) && !x_aux) return fail(SOM_ERR_ARG, "som_backward_dx: the latent staging's aux vector is required");
   som::EpiParams e{};
   e.sum = row_part; e.sum_n = static_cast<int>(n_row_parts); e.sum_ld_m = n_row_parts; e.sum_ld_j = 1;
-  e.aux = x_aux; e.g_dev = g_dev; e.mode = mode; e.accumulate = accumulate;
+  e.aux = x_aux; e.g_dev = g_dev; e.mode = dmode; e.accumulate = accumulate;
   e.src = x; e.lds = ldx; e.out = dx; e.ldo = lddx;
+  if (f16) { e.grad_scale = x_aux + 2 * B; e.grad_inv_s = row_part + B * n_row_parts; }   // 2^e_b, 1 / S (loss kernel)
   return launch_gemm(som::EPI_GRAD, r_hi, r_lo, ldr, 0, w_hi, w_lo, ld_stage, 1, B, D, K, 0, 0, 3, e, ws, ws_floats,
-                     as_stream(stream), sm_limit);
+                     as_stream(stream), sm_limit, f16);
 }
 
 // Both gradient GEMMs in ONE persistent CTA-pair launch: their tiles form one work list (dW tiles first) that stream-K
@@ -1788,8 +2119,11 @@ int som_backward_fused(const float* r_hi, const float* r_lo, int64_t ldr, const 
   if (!W || !col_part || !x || !row_part || n_row_parts <= 0 || n_col_parts <= 0 || !g_dev || !dW || !dx || ldw < D ||
       lddw < D || ldx < D || lddx < D)
     return fail(SOM_ERR_ARG, "som_backward_fused: bad argument");
-  if (mode != SOM_MODE_EUCLIDEAN && mode != SOM_MODE_COSINE) return fail(SOM_ERR_ARG, "som_backward_fused: bad mode");
-  if (mode == SOM_MODE_COSINE && (!w_aux || !x_aux)) return fail(SOM_ERR_ARG, "som_backward_fused: cosine needs the reciprocal norms");
+  if (!mode_ok(mode)) return fail(SOM_ERR_ARG, "som_backward_fused: bad mode");
+  const int mode_full = mode;
+  const int f16 = mode_f16(mode);
+  mode &= 1;
+  if ((mode == SOM_MODE_COSINE || f16) && (!w_aux || !x_aux)) return fail(SOM_ERR_ARG, "som_backward_fused: the aux vectors of both stagings are required");
   // Counted (two-phase) launches use ALL SMs for the first GEMM and at most sm_limit for the second: the pairs beyond
   // the limit get an empty share of phase 1, exit, and their SMs are free exactly when the exchange kernel that the
   // first GEMM's completion starts needs them.  Uncounted launches: sm_limit bounds the whole grid.
@@ -1803,11 +2137,15 @@ int som_backward_fused(const float* r_hi, const float* r_lo, int64_t ldr, const 
   p[0].e.sum = col_part; p[0].e.sum_n = static_cast<int>(n_col_parts); p[0].e.sum_ld_m = 1; p[0].e.sum_ld_j = K;
   p[0].e.aux = w_aux; p[0].e.g_dev = g_dev; p[0].e.mode = mode; p[0].e.accumulate = accumulate_dw;
   p[0].e.src = W; p[0].e.lds = ldw; p[0].e.out = dW; p[0].e.ldo = lddw;
+  p[0].f16 = f16;
+  if (f16) { p[0].e.grad_scale = w_aux + 2 * K; p[0].e.grad_inv_s = col_part + n_col_parts * K; }
   // dx[B,D] = R[B,K] . W[K,D]: A = R K-major, B = W~ MN-major
   p[1] = Problem{r_hi, r_lo, ldr, 0, w_hi, w_lo, ld_stage, 1, B, D, K, som::EpiParams{}};
   p[1].e.sum = row_part; p[1].e.sum_n = static_cast<int>(n_row_parts); p[1].e.sum_ld_m = n_row_parts; p[1].e.sum_ld_j = 1;
   p[1].e.aux = x_aux; p[1].e.g_dev = g_dev; p[1].e.mode = mode; p[1].e.accumulate = 0;
   p[1].e.src = x; p[1].e.lds = ldx; p[1].e.out = dx; p[1].e.ldo = lddx;
+  p[1].f16 = f16;
+  if (f16) { p[1].e.grad_scale = x_aux + 2 * B; p[1].e.grad_inv_s = row_part + B * n_row_parts; }
 
   // common tile width: the cheapest stream-K schedule of the joint work list (cost model of pick_tile)
   const int forced_bn = g_bn_override.load();
@@ -1818,11 +2156,13 @@ int som_backward_fused(const float* r_hi, const float* r_lo, int64_t ldr, const 
   // exchange can start) after about half of the launch.
   if (phased && count_dx) std::swap(p[0], p[1]);
   if (ws && g_streamk.load() >= 0 && g_cg_override.load() != 1 && B > 128 && K > 128) {
+    const int pmn = som::gemm_panel_mn(f16), bk = som::gemm_bk(f16);
     for (int bn : {256, 192, 128, 64}) {
       if (forced_bn && bn != forced_bn) continue;
+      if ((bn / 2) % pmn != 0) continue;              // both B operands are MN-major: whole panels per CTA
       int64_t units = 0, nkb_max = 1, units_min = INT64_MAX;
       for (int i = 0; i < 2; ++i) {
-        const int64_t nkb = (p[i].Kred + som::BK - 1) / som::BK;
+        const int64_t nkb = (p[i].Kred + bk - 1) / bk;
         const int64_t u = ((p[i].M + 255) / 256) * ((p[i].N + bn - 1) / bn) * nkb;
         units += u;
         units_min = std::min(units_min, u);
@@ -1831,17 +2171,17 @@ int som_backward_fused(const float* r_hi, const float* r_lo, int64_t ldr, const 
       const int64_t workers = phased ? streamk_workers(2 * units_min, slots, bn, ws_floats, 2)
                                      : streamk_workers(units, slots, bn, ws_floats);
       if (workers < 2) continue;
-      const bool panel_loads = D % 32 != 0 || (bn / 2) % 32 != 0 || !g_tma3d.load();    // B of both GEMMs has extent D
+      const bool panel_loads = D % pmn != 0 || !g_tma3d.load();    // B of both GEMMs has extent D
       const double cost = streamk_cost_ns(units, workers, nkb_max, bn, panel_loads);
       if (cost < best_cost) { best_cost = cost; best_bn = bn; best_workers = workers; }
     }
   }
   if (best_bn == 0) {
     if (int rc = som_backward_dw(r_hi, r_lo, ldr, x_hi, x_lo, ld_stage, W, ldw, col_part, n_col_parts, w_aux, g_dev, B, K,
-                                 D, mode, dW, lddw, accumulate_dw, sm_limit, ws, ws_floats, stream))
+                                 D, mode_full, dW, lddw, accumulate_dw, sm_limit, ws, ws_floats, stream))
       return rc;
     return som_backward_dx(r_hi, r_lo, ldr, w_hi, w_lo, ld_stage, x, ldx, row_part, n_row_parts, x_aux, g_dev, B, K, D,
-                           mode, dx, lddx, 0, sm_limit, ws, ws_floats, stream);
+                           mode_full, dx, lddx, 0, sm_limit, ws, ws_floats, stream);
   }
   int ph1 = 0;
   if (dw_done) {
@@ -1901,22 +2241,27 @@ int som_adamw_step(float* W, int64_t ldw, const float* dW, int64_t lddw, float* 
     return fail(SOM_ERR_ARG, "som_adamw_step: bad argument");
   if (K > 0x7fffffffLL) return fail(SOM_ERR_ARG, "som_adamw_step: too many rows");
   if (w_hi) {
-    if (!w_lo || !w_aux || ld_stage < D || (ld_stage & 3) != 0 ||
+    if (!mode_ok(mode)) return fail(SOM_ERR_ARG, "som_adamw_step: bad mode");
+    if (!w_lo || !w_aux || ld_stage < D || (ld_stage & (mode_f16(mode) ? 7 : 3)) != 0 ||
         ((reinterpret_cast<uintptr_t>(w_hi) | reinterpret_cast<uintptr_t>(w_lo)) & 15) != 0)
       return fail(SOM_ERR_ARG, "som_adamw_step: bad staging buffers");
-    if (mode != SOM_MODE_EUCLIDEAN && mode != SOM_MODE_COSINE) return fail(SOM_ERR_ARG, "som_adamw_step: bad mode");
   }
   AdamHyper hp{beta1, beta2, eps, weight_decay};
-  if (D <= 1024)
-    SOM_CUDA(launch_kernel(adamw_stage_kernel<32>, dim3(static_cast<unsigned>((K + 7) / 8)), dim3(256), 0, as_stream(stream),
-                           W, static_cast<long long>(ldw), dW, static_cast<long long>(lddw), m, v,
-                           static_cast<long long>(ldm), static_cast<long long>(K), static_cast<int>(D), hp_dev, hp, mode,
-                           w_hi, w_lo, static_cast<long long>(ld_stage), w_aux));
-  else
-    SOM_CUDA(launch_kernel(adamw_stage_kernel<256>, dim3(static_cast<unsigned>(K)), dim3(256), 0, as_stream(stream), W,
-                           static_cast<long long>(ldw), dW, static_cast<long long>(lddw), m, v, static_cast<long long>(ldm),
-                           static_cast<long long>(K), static_cast<int>(D), hp_dev, hp, mode, w_hi, w_lo,
-                           static_cast<long long>(ld_stage), w_aux));
+  const int dmode = mode & 1;
+  auto launch = [&](auto kernel, unsigned grid) {
+    return launch_kernel(kernel, dim3(grid), dim3(256), 0, as_stream(stream), W, static_cast<long long>(ldw), dW,
+                         static_cast<long long>(lddw), m, v, static_cast<long long>(ldm), static_cast<long long>(K),
+                         static_cast<int>(D), hp_dev, hp, dmode, w_hi, w_lo, static_cast<long long>(ld_stage), w_aux);
+  };
+  const bool f16 = w_hi && mode_f16(mode);
+  if (D <= 1024) {
+    const unsigned grid = static_cast<unsigned>((K + 7) / 8);
+    if (f16) SOM_CUDA(launch(adamw_stage_kernel<32, true>, grid));
+    else     SOM_CUDA(launch(adamw_stage_kernel<32, false>, grid));
+  } else {
+    if (f16) SOM_CUDA(launch(adamw_stage_kernel<256, true>, static_cast<unsigned>(K)));
+    else     SOM_CUDA(launch(adamw_stage_kernel<256, false>, static_cast<unsigned>(K)));
+  }
   g_launches.fetch_add(1);
   return SOM_OK;
 }
@@ -1979,6 +2324,18 @@ int som_debug_gemm(const float* a_hi, const float* a_lo, int64_t lda, int a_mn, 
   e.out = C; e.ldo = ldc;
   return launch_gemm(som::EPI_RAW, a_hi, a_lo, lda, a_mn, b_hi, b_lo, ldb, b_mn, M, N, Kred, bn, kchunk, passes, e,
                      ws, ws_floats, as_stream(stream));
+}
+
+// The same mainloop on fp16 operands (hi / lo point to __half matrices, lda / ldb in halves, multiples of 8).
+int som_debug_gemm_f16(const void* a_hi, const void* a_lo, int64_t lda, int a_mn, const void* b_hi, const void* b_lo,
+                       int64_t ldb, int b_mn, int64_t M, int64_t N, int64_t Kred, int bn, int kchunk, int passes, float* C,
+                       int64_t ldc, float* ws, int64_t ws_floats, void* stream) {
+  if (!C || ldc < N) return fail(SOM_ERR_ARG, "som_debug_gemm_f16: bad output");
+  som::EpiParams e{};
+  e.out = C; e.ldo = ldc;
+  return launch_gemm(som::EPI_RAW, static_cast<const float*>(a_hi), static_cast<const float*>(a_lo), lda, a_mn,
+                     static_cast<const float*>(b_hi), static_cast<const float*>(b_lo), ldb, b_mn, M, N, Kred, bn, kchunk,
+                     passes, e, ws, ws_floats, as_stream(stream), 0, 1);
 }
 
 }  // extern "C"

@@ -505,7 +505,7 @@ class PrototypeShardedSOM(SOMLayer):
             self.invalidate_staging()
             raise
         reduce_packed_min(state.packed, self.group)          # exchange step 1: B x 8 bytes over NVLink
-        bmu = ops.bmu_decode(state.packed, self.k_total)
+        bmu = ops.bmu_decode(state.packed, self.k_total, state=state)
         if not want_dist:
             return None, bmu
         state.x_in, state.W_in = x, self.prototypes

@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import contextlib
 import ctypes
+import os
 
 import torch
 
@@ -25,6 +26,15 @@ from . import _lib
 from ._lib import SomError, check, ptr, stream_ptr
 
 MODE = {"euclidean": 0, "cosine": 1}
+# operand precision, OR-ed into the mode word of every C-ABI call (include/som_b200.h: SOM_PREC_FP16X3)
+PREC = {"tf32x3": 0, "fp16x3": 16}
+PREC_FP16X3 = 16
+# what a layer without an explicit ``precision`` attribute computes in (environment override for A/B runs)
+DEFAULT_PRECISION = os.environ.get("SOM_B200_PRECISION", "tf32x3")
+
+
+def is_f16(mode: int) -> bool:
+    return bool(mode & PREC_FP16X3)
 
 # bench.py sets this to a list to get per-launch CUDA-event timings of the three tensor-core GEMMs
 # (entries: (name, start_event, end_event) recorded on the launching stream).
@@ -46,6 +56,10 @@ def _gemm(name, call):
 
 def _pad4(n: int) -> int:
     return (n + 3) // 4 * 4
+
+
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
 
 
 def _guard(device):
@@ -81,25 +95,48 @@ def _rowmajor(t: torch.Tensor) -> torch.Tensor:
 
 
 class Staging:
-    """tf32 hi/lo split of a row-major [rows, dim] matrix plus its per-row aux vector (|row|^2 for euclidean,
-    1/max(|row|, eps) for cosine), carved out of one flat allocation: hi | lo | aux."""
-    __slots__ = ("buf", "rows", "dim", "ld", "mode", "hi", "lo", "aux", "key", "from_optimizer")
+    """Staged form of a row-major [rows, dim] matrix, carved out of one flat allocation: hi | lo | aux.
+
+    * 3xTF32 (default): hi / lo are the exact tf32 split in fp32 containers, row pitch ``ld`` = pad4(dim) floats; aux holds
+      one float per row (|row|^2 for euclidean, 1/max(|row|, eps) for cosine).
+    * 3xFP16 (``mode & PREC_FP16X3``): hi / lo are fp16 matrices of the row-scaled operand, row pitch ``ld`` = pad8(dim)
+      halves; aux holds 3 * rows + 4 floats: aux | 2^-e | 2^e | 4 statistics words (include/som_b200.h)."""
+    __slots__ = ("buf", "rows", "dim", "ld", "mode", "hi", "lo", "aux", "key", "from_optimizer", "aux_off")
 
     def __init__(self, rows: int, dim: int, mode: int, device):
         if rows <= 0 or dim <= 0:
             raise ValueError("empty operand")
         self.rows, self.dim, self.mode = rows, dim, mode
-        self.ld = _pad4(dim)
-        n = rows * self.ld
-        self.buf = torch.empty((2 * n + rows,), device=device, dtype=torch.float32)
-        base = self.buf.data_ptr()
-        self.hi, self.lo, self.aux = base, base + 4 * n, base + 8 * n
+        if is_f16(mode):
+            self.ld = _pad8(dim)
+            n = rows * self.ld                # halves per matrix = n / 2 floats; hi + lo together n floats
+            self.buf = torch.empty((n + 3 * rows + 4,), device=device, dtype=torch.float32)
+            base = self.buf.data_ptr()
+            self.hi, self.lo, self.aux = base, base + 2 * n, base + 4 * n
+            self.aux_off = n
+        else:
+            self.ld = _pad4(dim)
+            n = rows * self.ld
+            self.buf = torch.empty((2 * n + rows,), device=device, dtype=torch.float32)
+            base = self.buf.data_ptr()
+            self.hi, self.lo, self.aux = base, base + 4 * n, base + 8 * n
+            self.aux_off = 2 * n
         self.key = None                       # identity of the tensor version staged here (prototype cache)
         self.from_optimizer = False           # filled by the fused optimizer kernel for the parameter version in `key`
 
     def aux_tensor(self) -> torch.Tensor:
+        """The per-row aux vector (norms / reciprocal norms)."""
+        return self.buf[self.aux_off:self.aux_off + self.rows]
+
+    def scale_tensor(self) -> torch.Tensor:
+        """3xFP16 only: the 2^e row scales."""
+        return self.buf[self.aux_off + 2 * self.rows:self.aux_off + 3 * self.rows]
+
+    def halves(self):
+        """3xFP16 only: (hi, lo) as [rows, ld] fp16 views."""
         n = self.rows * self.ld
-        return self.buf[2 * n:]
+        h = self.buf[:n].view(torch.float16)
+        return h[:n].view(self.rows, self.ld), h[n:2 * n].view(self.rows, self.ld)
 
 
 def stage_rows(src: torch.Tensor, mode: int) -> Staging:
@@ -166,7 +203,10 @@ def forward(x: torch.Tensor, W: torch.Tensor, mode: int, ws: Staging | None = No
             check(_gemm("fwd", lambda: L.som_fwd_distances(xs.hi, xs.lo, xs.ld, xs.aux, ws.hi, ws.lo, ws.ld, ws.aux,
                                                            B, K, D, mode, idx_offset, ptr(dist_buf), ldd, ptr(packed),
                                                            gws, gws_n, sp)), "som_fwd_distances")
-            if bmu is not None:
+            if bmu is not None and is_f16(mode):
+                check(L.som_bmu_decode_scaled(ptr(packed), B, k_total if k_total is not None else K, ptr(bmu), None,
+                                              xs.aux, ws.aux, K, mode, sp), "som_bmu_decode_scaled")
+            elif bmu is not None:
                 check(L.som_bmu_decode(ptr(packed), B, k_total if k_total is not None else K, ptr(bmu), None, sp),
                       "som_bmu_decode")
     st = ForwardState()
@@ -182,13 +222,19 @@ def forward(x: torch.Tensor, W: torch.Tensor, mode: int, ws: Staging | None = No
     return st, bmu
 
 
-def bmu_decode(packed: torch.Tensor, k_total: int, want_min: bool = False):
+def bmu_decode(packed: torch.Tensor, k_total: int, want_min: bool = False, state=None):
+    """packed (key, index) minima -> int64 BMUs.  ``state``: the forward these minima belong to; with 3xFP16 stagings the
+    decode also leaves the scaling statistic of the backward staging in the latent staging (som_bmu_decode_scaled)."""
     B = packed.shape[0]
     dev = packed.device
     bmu = torch.empty((B,), device=dev, dtype=torch.int64)
     mn = torch.empty((B,), device=dev, dtype=torch.float32) if want_min else None
     with _guard(dev):
-        check(_lib.lib().som_bmu_decode(ptr(packed), B, k_total, ptr(bmu), ptr(mn), stream_ptr(dev)), "som_bmu_decode")
+        if state is not None and is_f16(state.mode):
+            check(_lib.lib().som_bmu_decode_scaled(ptr(packed), B, k_total, ptr(bmu), ptr(mn), state.xs.aux, state.ws.aux,
+                                                   state.K, state.mode, stream_ptr(dev)), "som_bmu_decode_scaled")
+        else:
+            check(_lib.lib().som_bmu_decode(ptr(packed), B, k_total, ptr(bmu), ptr(mn), stream_ptr(dev)), "som_bmu_decode")
     return (bmu, mn) if want_min else bmu
 
 
@@ -270,21 +316,26 @@ class FusedLossFn(torch.autograd.Function):
                            "prototype gradient would never be exchanged (use DataParallelSOM.reduce_accumulator() "
                            "after the last chunk and detach the hook, or drop the accumulator)")
         loss = torch.empty((), device=dev, dtype=torch.float32)
-        ldr = _pad4(K)
+        f16 = is_f16(state.mode)
+        ldr = _pad8(K) if f16 else _pad4(K)
         with _guard(dev):
             scratch = _loss_scratch(dev, int(L.som_loss_fused_scratch_floats(B, K)))
             if want_grad:
                 nrp, ncp = loss_parts(B, K, dev)
-                rbuf = torch.empty((2 * B * ldr + B * nrp + ncp * K,), device=dev, dtype=torch.float32)
+                # R hi | R lo | row parts (+ 4: 1 / S of the fp16 staging) | column parts (+ 4)
+                r_floats = B * ldr // 2 if f16 else B * ldr          # floats per R matrix (fp16: two halves per float)
+                row_floats = _pad4(B * nrp + 4)
+                rbuf = torch.empty((2 * r_floats + row_floats + ncp * K + 4,), device=dev, dtype=torch.float32)
                 base = rbuf.data_ptr()
-                r_hi, r_lo = base, base + 4 * B * ldr
-                row_part = base + 8 * B * ldr
-                col_part = row_part + 4 * B * nrp
+                r_hi, r_lo = base, base + 4 * r_floats
+                row_part = base + 8 * r_floats
+                col_part = row_part + 4 * row_floats
             else:
                 rbuf, r_hi, r_lo, row_part, col_part, nrp, ncp = None, None, None, None, None, 0, 0
             check(L.som_loss_fused(ptr(state.dist_buf), state.ldd, ptr(bmu), ptr(grid_pos), int(grid_dims[0]),
                                    int(grid_dims[1]), B, K, k_offset, ptr(T_dev),
                                    inv_count, state.mode, r_hi, r_lo, ldr, row_part, col_part, ptr(scratch), ptr(loss),
+                                   state.xs.aux if f16 else None, state.ws.aux if f16 else None,
                                    stream_ptr(dev)), "som_loss_fused")
         ctx.state, ctx.rbuf, ctx.ptrs, ctx.ldr = state, rbuf, (r_hi, r_lo, row_part, nrp, col_part, ncp), ldr
         ctx.x_dtype, ctx.x_shape, ctx.dw_hook = x.dtype, x.shape, dw_hook
@@ -428,6 +479,11 @@ class DistanceFn(torch.autograd.Function):
         dev = st.dist_buf.device
         L = _lib.lib()
         G = _rowmajor(_require_cuda_f32(g_dist, "grad_distances"))
+        xs, ws = st.xs, st.ws
+        if is_f16(mode):
+            # general path (an arbitrary upstream gradient of the distances): its kernels take tf32 stagings
+            mode &= 1
+            xs, ws = stage_rows(st.x, mode), stage_rows(st.W, mode)
         ldr = _pad4(K)
         r_hi = torch.empty((B, ldr), device=dev, dtype=torch.float32)
         r_lo = torch.empty((B, ldr), device=dev, dtype=torch.float32)
@@ -436,12 +492,12 @@ class DistanceFn(torch.autograd.Function):
         dx = dw = None
         with _guard(dev):
             sp = stream_ptr(dev)
-            check(L.som_bwd_coeffs(ptr(G), G.stride(0), ptr(st.dist_buf), st.ldd, B, K, mode, st.xs.aux, st.ws.aux,
+            check(L.som_bwd_coeffs(ptr(G), G.stride(0), ptr(st.dist_buf), st.ldd, B, K, mode, xs.aux, ws.aux,
                                    ptr(r_hi), ptr(r_lo), ldr, ptr(ax), ptr(bx), ptr(aw), ptr(bw), sp), "som_bwd_coeffs")
             gws, gws_n = gemm_workspace(dev)
             if ctx.needs_input_grad[0]:
                 dx = torch.empty((B, D), device=dev, dtype=torch.float32)
-                check(_gemm("dx", lambda: L.som_bwd_dx(ptr(r_hi), ptr(r_lo), ldr, st.ws.hi, st.ws.lo, st.ws.ld, ptr(st.x),
+                check(_gemm("dx", lambda: L.som_bwd_dx(ptr(r_hi), ptr(r_lo), ldr, ws.hi, ws.lo, ws.ld, ptr(st.x),
                                                        st.x.stride(0), ptr(ax), ptr(bx), B, K, D, ptr(dx), D,
                                                        gws, gws_n, sp)), "som_bwd_dx")
                 if dx.dtype != ctx.x_dtype:
@@ -449,7 +505,7 @@ class DistanceFn(torch.autograd.Function):
                 dx = dx.view(ctx.x_shape)
             if ctx.needs_input_grad[1]:
                 dw = torch.empty((K, D), device=dev, dtype=torch.float32)
-                check(_gemm("dw", lambda: L.som_bwd_dw(ptr(r_hi), ptr(r_lo), ldr, st.xs.hi, st.xs.lo, st.xs.ld, ptr(st.W),
+                check(_gemm("dw", lambda: L.som_bwd_dw(ptr(r_hi), ptr(r_lo), ldr, xs.hi, xs.lo, xs.ld, ptr(st.W),
                                                        st.W.stride(0), ptr(aw), ptr(bw), B, K, D, ptr(dw), D,
                                                        gws, gws_n, sp)), "som_bwd_dw")
         return dx, dw, None

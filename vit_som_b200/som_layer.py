@@ -118,6 +118,9 @@ class SOMLayer(_Base):
         # optional: rows of the WHOLE batch when it is fed in row chunks - som_loss then divides by batch_rows * K, so
         # the chunk losses (and their gradients) simply add up to the loss of the whole batch (None: rows of the call)
         self.batch_rows = None
+        # operand precision of the tensor-core contractions: "tf32x3" (3xTF32) or "fp16x3" (3xFP16 on row-scaled operands:
+        # the same 22-bit split at twice the tensor-core rate); None = ops.DEFAULT_PRECISION.  Both are fp32-accurate.
+        self.precision = som_hp.get("precision")
         self._dw_hook = None                                              # data-parallel wrapper: called with dW as soon as it is enqueued
         self._dw_out = None                                               # data-parallel wrapper: [K, D] buffer the dW GEMM writes (NVLS symmetric memory)
 
@@ -143,7 +146,10 @@ class SOMLayer(_Base):
             raise NotImplementedError(
                 "distance_fcn='manhattan' (DESOM, cdist p=1) is not a contraction and is out of scope of the "
                 "B200 hot path; use 'euclidean' or 'cosine'")
-        return ops.MODE[self.distance_fcn]
+        prec = getattr(self, "precision", None) or ops.DEFAULT_PRECISION
+        if prec not in ops.PREC:
+            raise ValueError(f"precision must be one of {sorted(ops.PREC)}, got {prec!r}")
+        return ops.MODE[self.distance_fcn] | ops.PREC[prec]
 
     def _staging_key(self, mode: int):
         W = self.prototypes
