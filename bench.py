@@ -273,6 +273,23 @@ class Env:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return t.tolist()
 
+    def _matmul_rate(self, dtype):
+        torch = self.torch
+        n = 8192
+        a = torch.randn(n, n, device=self.dev).to(dtype)
+        b = torch.randn(n, n, device=self.dev).to(dtype)
+        for _ in range(3):
+            torch.matmul(a, b)
+        best = float("inf")
+        for _ in range(10):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            torch.matmul(a, b)
+            e.record()
+            e.synchronize()
+            best = min(best, s.elapsed_time(e))
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
     def measure_tf32_peak(self):
         """Dense TF32 tensor-core rate of THIS GPU: torch.matmul (cuBLAS, allow_tf32) on 8192^3, best of 10 - the
         tensor roofline of a kind::tf32 kernel (a 3xTF32 product issues three of these per algorithmic MMA)."""
@@ -282,23 +299,17 @@ class Env:
         prev = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = True
         try:
-            n = 8192
-            a = torch.randn(n, n, device=self.dev)
-            b = torch.randn(n, n, device=self.dev)
-            for _ in range(3):
-                torch.matmul(a, b)
-            best = float("inf")
-            for _ in range(10):
-                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                s.record()
-                torch.matmul(a, b)
-                e.record()
-                e.synchronize()
-                best = min(best, s.elapsed_time(e))
-            self.tf32_peak = 2.0 * n ** 3 / (best * 1e-3) / 1e12
+            self.tf32_peak = self._matmul_rate(torch.float32)
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev
         return self.tf32_peak
+
+    def measure_fp16_peak(self):
+        """Dense fp16 tensor-core rate of THIS GPU (torch.matmul, fp16 in / fp32 accumulate, 8192^3, best of 10): the
+        tensor roofline of a kind::f16 kernel (a 3xFP16 product issues three of these per algorithmic MMA)."""
+        if getattr(self, "fp16_peak", None) is None:
+            self.fp16_peak = self._matmul_rate(self.torch.float16)
+        return self.fp16_peak
 
 
 def measure_som(env, name, wl, steps, warmup, sharded=False, with_e2e=False, with_roofline=True, clocks=None):
@@ -502,8 +513,9 @@ def measure_som(env, name, wl, steps, warmup, sharded=False, with_e2e=False, wit
             e.record()
             e.synchronize()
             tt.append(s.elapsed_time(e))
-        nbytes = 9 * K_local * D * 4            # reads W, dW, m, v; writes W, m, v, W_hi, W_lo
-        out["adamw"] = {"kernel": "adamw_stage_kernel (AdamW update + tf32 staging of the new prototypes)",
+        # reads W, dW, m, v; writes W, m, v and the staging W_hi, W_lo (fp32 containers, or fp16 under fp16x3)
+        nbytes = (8 if getattr(env, "precision", "tf32x3") == "fp16x3" else 9) * K_local * D * 4
+        out["adamw"] = {"kernel": "adamw_stage_kernel (AdamW update + operand staging of the new prototypes)",
                         "ms": statistics.median(ts), "algorithmic_bytes": nbytes,
                         "achieved_gbs": nbytes / (statistics.median(ts) * 1e-3) / 1e9,
                         "frac_of_hbm_peak": nbytes / (statistics.median(ts) * 1e-3) / 1e9 / env.peaks["hbm_gbs"],
@@ -585,9 +597,11 @@ def roofline_of(env, wl, res, traffic=None):
     peaks = env.peaks
     chunk, K_local = res["chunk"], res["K_local"]
     tf32_peak = env.measure_tf32_peak()
+    f16 = getattr(env, "precision", "tf32x3") == "fp16x3"
+    kind_peak = env.measure_fp16_peak() if f16 else tf32_peak      # dense rate of the instruction kind the kernels issue
     ms_per_step = res["total_ms"] / res["steps"]
     intensity = 0.75 * chunk * K_local / (chunk + K_local)
-    ridge = (tf32_peak / 3.0) * 1e12 / (peaks["hbm_gbs"] * 1e9)
+    ridge = (kind_peak / 3.0) * 1e12 / (peaks["hbm_gbs"] * 1e9)
     rows = B                                                  # per GPU: a shard scores ALL rows against its K_local prototypes
     step_flops = 6.0 * rows * K_local * D
     step_bytes = 4.0 * (2 * rows * D + 2 * K_local * D) + 8 * rows + 4
@@ -607,11 +621,22 @@ def roofline_of(env, wl, res, traffic=None):
     total_flops = sum(len(v) * per_gemm_flops * (2 if "+" in k else 1) for k, v in gemm_ms.items())
     achieved_tf = total_flops / (gemm_total_ms * 1e-3) / 1e12 if gemm_total_ms else 0.0
     step_tf = step_flops / (ms_per_step * 1e-3) / 1e12
+    # The bound of a 3-product split is a third of the dense rate of the instruction kind it issues.  Both bounds are
+    # reported: against the kind the kernels use (fp16x3: the measured fp16 rate; the driver's bf16 burst figure is the
+    # same datapath) and against the TF32 rate, which is what rounds 1-2 quoted (a 3xFP16 kernel may exceed THAT bound:
+    # it is the ceiling of the 3xTF32 formulation, not of the hardware).
+    basis = ("fp16 dense rate measured on this GPU in this run (torch.matmul fp16, 8192^3, best of 10); the kernels issue "
+             "tcgen05.mma.kind::f16, three per algorithmic MMA (3xFP16 on row-scaled operands)" if f16 else
+             "TF32 dense rate measured on this GPU in this run (torch.matmul allow_tf32, 8192^3, best of 10); the kernels "
+             "issue tcgen05.mma.kind::tf32, three per algorithmic MMA (3xTF32)")
+    basis += (f"; driver-measured bf16 burst {peaks['bf16_tflops']} TFLOP/s ({peaks['source']}), TF32 dense measured here "
+              f"{tf32_peak:.1f} TFLOP/s")
     return {
         "bound": "tensor", "kernel": "som_gemm3x_pair_kernel (forward launch + fused dW/dx launch)",
-        "achieved": achieved_tf, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved_tf / tf32_peak,
-        "peak_basis": "TF32 dense rate measured on this GPU in this run (torch.matmul allow_tf32, 8192^3, best of 10); "
-                      f"bf16 burst {peaks['bf16_tflops']} TFLOP/s ({peaks['source']}) / 2 = {peaks['bf16_tflops'] / 2:.1f}",
+        "precision": "fp16x3" if f16 else "tf32x3",
+        "achieved": achieved_tf, "peak": kind_peak, "unit": "TFLOP/s", "frac": achieved_tf / kind_peak,
+        "peak_basis": basis,
+        "frac_of_3x_bound": achieved_tf / (kind_peak / 3.0),
         "frac_of_3xtf32_bound": achieved_tf / (tf32_peak / 3.0),
         # the same against half of the driver-measured bf16 burst rate (the basis of round 1's fractions; cuBLAS' TF32
         # GEMM itself stays ~10 % below it)
@@ -620,21 +645,24 @@ def roofline_of(env, wl, res, traffic=None):
         "avg_launch_ms": gemm_total_ms / max(n_launch, 1),
         "per_gemm_ms": {k: sum(v) / len(v) for k, v in gemm_ms.items()},
         "gemm_share_of_step": (per_step_gemm_ms / ms_per_step) if per_step_gemm_ms else None,
-        "whole_step": {"achieved": step_tf, "frac": step_tf / tf32_peak, "frac_of_3xtf32_bound": step_tf / (tf32_peak / 3.0),
+        "whole_step": {"achieved": step_tf, "frac": step_tf / kind_peak, "frac_of_3x_bound": step_tf / (kind_peak / 3.0),
+                       "frac_of_3xtf32_bound": step_tf / (tf32_peak / 3.0),
                        "frac_of_3xtf32_bound_vs_bf16_half": step_tf / (peaks["bf16_tflops"] / 2.0 / 3.0),
                        "algorithmic_flops_per_step": step_flops},
         "traffic": traffic,
     }
 
 
-def load_traffic(name, world):
+def load_traffic(name, world, precision="tf32x3"):
     """DRAM bytes per launch of the dominant kernel from an `ncu --set full` capture of THIS workload at THIS GPU count
-    (profiles/traffic_r02.json, key "<workload>@n<N>"); null when no such capture exists."""
+    and operand precision (profiles/traffic_r02.json, key "<workload>@n<N>" for tf32x3, "<workload>@n<N>@fp16x3"
+    otherwise); null when no such capture exists."""
     path = os.path.join(ROOT, "profiles", "traffic_r02.json")
     if not os.path.exists(path):
         return None
+    key = f"{name}@n{world}" + ("" if precision == "tf32x3" else f"@{precision}")
     with open(path) as f:
-        return json.load(f).get(f"{name}@n{world}", {}).get("dram_bytes_per_launch")
+        return json.load(f).get(key, {}).get("dram_bytes_per_launch")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -832,7 +860,7 @@ def measure_vit_som(env, tag, dataset, map_size, batch, steps, warmup):
     out = {"workload": f"{tag}: ViT-SOM-cls {dataset}-shaped {size}x{size}x{chans}, {map_size[0]}x{map_size[1]} map, "
                        f"batch {batch} per GPU (emb 192, depth 12, heads 3, patch 4; cosine SOM on {D}-dim patch latents)",
            "img_per_s": batch * world / (ms * 1e-3), "ms_per_step": ms, "steps": steps, "n_gpus": world,
-           "precision": "bf16 autocast ViT (SDPA), fp32-accurate (3xTF32) SOM layer, fp32 AdamW",
+           "precision": f"bf16 autocast ViT (SDPA), fp32-accurate ({getattr(env, 'precision', 'tf32x3')}) SOM layer, fp32 AdamW",
            "step": "forward + CE/SOM loss (device-side gamma ramp, strided SOM input) + backward + AdamW (ViT) + fused "
                    "AdamW (prototypes); " + ("one CUDA graph per step" if graph is not None else "eager launches"),
            "parallelism": "single GPU" if world == 1 else
@@ -869,6 +897,8 @@ def main():
                     help="prototype-sharded: do not overlap the last chunk's dx exchange inside its backward launch")
     ap.add_argument("--no-extras", action="store_true", help="headline only: skip cfg5, ViT-SOM img/s and the parity check")
     ap.add_argument("--no-vit", action="store_true", help="skip the ViT-SOM img/s records")
+    ap.add_argument("--precision", default=None, choices=["fp16x3", "tf32x3"],
+                    help="operand precision of the SOM layer's tensor-core contractions (default: the library default)")
     args = ap.parse_args()
     wl = list(WORKLOADS[args.workload])
     if args.distance:
@@ -881,6 +911,10 @@ def main():
     torch, dist = env.torch, env.dist
     world, rank, dev = env.world, env.rank, env.dev
     desc, B, ms, D, T, fcn = wl
+    from vit_som_b200 import ops as _ops
+    if args.precision:
+        _ops.DEFAULT_PRECISION = args.precision           # every layer built below follows it
+    env.precision = _ops.DEFAULT_PRECISION
     sharded = world > 1 and (args.shard == "prototypes" or (args.shard == "auto" and args.workload == "cfg5"))
 
     parity = None
@@ -907,7 +941,7 @@ def main():
                     "parallelism": workload_config("cfg5", c5, world, r5["chunk"], world > 1)["parallelism"],
                     "row_chunk": r5["chunk"], "cuda_graph": r5["graph"], "launches_per_step": r5["launches_per_step"],
                     "dx_exchange": ("NVLS multimem kernel" if r5["nvls"] else "NCCL all-reduce") if world > 1 else None,
-                    "roofline": roofline_of(env, c5, r5, load_traffic("cfg5", world))}
+                    "roofline": roofline_of(env, c5, r5, load_traffic("cfg5", world, env.precision))}
         if not args.no_vit:
             vit = {}
             for tag, dataset, msz, bsz in (("cfg3", "cifar-10", (4, 4), 128), ("cfg4", "tiny-imagenet", (40, 40), 512)):
@@ -954,10 +988,12 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K_, "warmup": head["warmup"],
         "ms_per_step": total_ms / K_, "higher_is_better": True, "scaling": "strong" if head["sharded"] else "weak",
         "vs_baseline": None,
-        "dtype": "fp32 (3xTF32 tensor-core products, fp32 accumulate)", "data": "synthetic",
+        "dtype": ("fp32 (3xFP16 tensor-core products on row-scaled operands, fp32 accumulate)" if env.precision == "fp16x3"
+                  else "fp32 (3xTF32 tensor-core products, fp32 accumulate)"),
+        "precision": env.precision, "data": "synthetic",
         "config": workload_config(args.workload, wl, world, head["chunk"], head["sharded"]),
         "cuda_graph": head["graph"],
-        "roofline": roofline_of(env, wl, head, load_traffic(args.workload, world)),
+        "roofline": roofline_of(env, wl, head, load_traffic(args.workload, world, env.precision)),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "h2d_gbs_per_gpu": h2d * K_ / (e2e_ms * 1e-3) / 1e9, "host_pinning": env.numa,
                 "path": head["e2e_path"]},

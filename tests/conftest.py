@@ -30,3 +30,23 @@ def cuda_device():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+# Every GPU test module runs under both operand precisions of the tensor-core contractions (3xTF32 and 3xFP16): the
+# modules ask for the fixture with `pytest.mark.usefixtures("som_precision")`, layers without an explicit `precision`
+# attribute follow ops.DEFAULT_PRECISION.
+PRECISIONS = ["tf32x3", "fp16x3"]
+
+
+def pytest_generate_tests(metafunc):
+    if "som_precision" in metafunc.fixturenames:
+        metafunc.parametrize("som_precision", PRECISIONS, indirect=True)
+
+
+@pytest.fixture
+def som_precision(request):
+    from vit_som_b200 import ops
+    old = ops.DEFAULT_PRECISION
+    ops.DEFAULT_PRECISION = request.param
+    yield request.param
+    ops.DEFAULT_PRECISION = old

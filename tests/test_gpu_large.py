@@ -16,7 +16,7 @@ import torch
 from oracle import som_oracle as O
 from oracle.ref_import import make_config
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("som_precision")]
 
 LOSS_TOL = 1e-5
 GRAD_TOL = 1e-5

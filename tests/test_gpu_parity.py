@@ -14,7 +14,7 @@ from conftest import golden_names, load_golden
 from oracle import som_oracle as O
 from oracle.ref_import import make_config
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("som_precision")]
 
 LOSS_TOL = 1e-5     # relative, north_star
 GRAD_TOL = 1e-5     # norm-wise relative, north_star

@@ -17,7 +17,7 @@ import torch
 from oracle import som_oracle as O
 from oracle.ref_import import make_config
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("som_precision")]
 
 LOSS_TOL = 1e-5
 GRAD_TOL = 1e-5
@@ -308,10 +308,17 @@ def test_fused_adamw_matches_torch(fcn, shape, cuda_device):
     fresh = ops.stage_rows(ours.prototypes.detach(), ours._mode())
     torch.cuda.synchronize()
     n = ws.rows * ws.ld
-    assert O.rel_err((ws.buf[:n] + ws.buf[n:2 * n]).cpu().numpy(), (fresh.buf[:n] + fresh.buf[n:2 * n]).cpu().numpy()) < 1e-6
+    assert O.rel_err(ws.dense().cpu().numpy(), fresh.dense().cpu().numpy()) < 1e-6
     assert O.rel_err(ws.aux_tensor().cpu().numpy(), fresh.aux_tensor().cpu().numpy()) < 1e-6
-    hi = ws.buf[:n].view(torch.int32)
-    assert int((hi & 0x1FFF).abs().max().item()) == 0            # hi parts are exact tf32 values (13 low mantissa bits clear)
+    if ops.is_f16(ws.mode):
+        # row scales are powers of two that lift the row maximum into [2^14, 2^15)
+        sc = ws.scale_tensor()
+        assert torch.equal(sc, torch.exp2(torch.log2(sc).round()))
+        top = ws.halves()[0].float().abs().amax(dim=1)
+        assert float(top.min()) >= 2.0 ** 14 * 0.999 and float(top.max()) <= 2.0 ** 15
+    else:
+        hi = ws.buf[:n].view(torch.int32)
+        assert int((hi & 0x1FFF).abs().max().item()) == 0        # hi parts are exact tf32 values (13 low mantissa bits clear)
     # and the next forward uses it (no W staging in the step) with the same results as a freshly staged layer
     x = torch.randn(B, D, device="cuda")
     ours.eval()

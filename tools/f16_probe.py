@@ -14,6 +14,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vit_som_b200 import _lib, ops  # noqa: E402
 
 L = _lib.lib()
+if os.environ.get("SOM_KCHUNK"):
+    L.som_set_tuning(0, int(os.environ["SOM_KCHUNK"]))     # k-blocks per accumulation chain (the pair kernel uses half)
 dev = torch.device("cuda:0")
 sp = lambda: torch.cuda.current_stream().cuda_stream  # noqa: E731
 

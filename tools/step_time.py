@@ -1,6 +1,6 @@
 """Per-kernel timing of one SOM step through the production C-ABI entry points (run on a B200 through gpurun).
 
-    python tools/step_time.py [B K_rows K_cols D [euclidean|cosine]]
+    python tools/step_time.py [B K_rows K_cols D [euclidean|cosine [tf32x3|fp16x3]]]
 
 Every entry point is launched `iters` times back to back behind a GPU-side sleep (so the events see GPU time
 only, L2-warm) and, for the CTA-pair GEMMs, once more with phase stamps.
@@ -50,7 +50,9 @@ def main():
     a = sys.argv[1:]
     B, kr, kc, D = (int(a[0]), int(a[1]), int(a[2]), int(a[3])) if len(a) >= 4 else (1024, 40, 40, 3136)
     fcn = a[4] if len(a) > 4 else "euclidean"
-    mode = ops.MODE[fcn]
+    prec = a[5] if len(a) > 5 else ops.DEFAULT_PRECISION
+    mode = ops.MODE[fcn] | ops.PREC[prec]
+    f16 = ops.is_f16(mode)
     K = kr * kc
     L = _lib.lib()
     sp = _lib.stream_ptr
@@ -66,9 +68,12 @@ def main():
     packed = torch.empty(B, dtype=torch.int64, device="cuda")
     bmu = torch.empty(B, dtype=torch.int64, device="cuda")
     nrp, ncp = ops.loss_parts(B, K, x.device)                  # partial-sum tables of the loss kernel
-    rbuf = torch.empty(2 * B * ldd + B * nrp + ncp * K, device="cuda")
-    r_hi, r_lo = rbuf.data_ptr(), rbuf.data_ptr() + 4 * B * ldd
-    row_sum, col_sum = rbuf.data_ptr() + 8 * B * ldd, rbuf.data_ptr() + 8 * B * ldd + 4 * B * nrp
+    ldr = (K + 7) // 8 * 8 if f16 else ldd                     # fp16: R is a pair of half matrices
+    r_floats = B * ldr // 2 if f16 else B * ldr
+    row_floats = (B * nrp + 4 + 3) // 4 * 4
+    rbuf = torch.empty(2 * r_floats + row_floats + ncp * K + 4, device="cuda")
+    r_hi, r_lo = rbuf.data_ptr(), rbuf.data_ptr() + 4 * r_floats
+    row_sum, col_sum = rbuf.data_ptr() + 8 * r_floats, rbuf.data_ptr() + 8 * r_floats + 4 * row_floats
     loss = torch.empty((), device="cuda")
     scratch = torch.zeros(1 << 16, device="cuda")
     dx, dw = torch.empty(B, D, device="cuda"), torch.empty(K, D, device="cuda")
@@ -96,19 +101,24 @@ def main():
     timed("GEMM fwd (argmin only)", lambda: chk(L.som_fwd_distances(
         xs.hi, xs.lo, xs.ld, xs.aux, ws.hi, ws.lo, ws.ld, ws.aux, B, K, D, mode, 0, None, ldd,
         packed.data_ptr(), wsp, wsn, sp()), "fwd"), stamps=True)
-    total += timed("decode", lambda: chk(L.som_bmu_decode(packed.data_ptr(), B, K, bmu.data_ptr(), None, sp()), "dec"))
+    if f16:
+        total += timed("decode + R scale statistic", lambda: chk(L.som_bmu_decode_scaled(
+            packed.data_ptr(), B, K, bmu.data_ptr(), None, xs.aux, ws.aux, K, mode, sp()), "dec"))
+    else:
+        total += timed("decode", lambda: chk(L.som_bmu_decode(packed.data_ptr(), B, K, bmu.data_ptr(), None, sp()), "dec"))
     total += timed("loss + coeffs", lambda: chk(L.som_loss_fused(
         dist.data_ptr(), ldd, bmu.data_ptr(), pos.data_ptr(), kr if SQUARE else 0, kc if SQUARE else 0, B, K, 0,
         T.data_ptr(), 1.0 / (B * K), mode, r_hi, r_lo,
-        ldd, row_sum, col_sum, scratch.data_ptr(), loss.data_ptr(), sp()), "loss"))
+        ldr, row_sum, col_sum, scratch.data_ptr(), loss.data_ptr(), xs.aux if f16 else None, ws.aux if f16 else None,
+        sp()), "loss"))
     total += timed("GEMM dW", lambda: chk(L.som_backward_dw(
-        r_hi, r_lo, ldd, xs.hi, xs.lo, xs.ld, W.data_ptr(), D, col_sum, ncp, ws.aux, g.data_ptr(), B, K, D, mode,
+        r_hi, r_lo, ldr, xs.hi, xs.lo, xs.ld, W.data_ptr(), D, col_sum, ncp, ws.aux, g.data_ptr(), B, K, D, mode,
         dw.data_ptr(), D, 0, 0, wsp, wsn, sp()), "dw"), stamps=True)
     total += timed("GEMM dx", lambda: chk(L.som_backward_dx(
-        r_hi, r_lo, ldd, ws.hi, ws.lo, ws.ld, x.data_ptr(), D, row_sum, nrp, xs.aux, g.data_ptr(), B, K, D, mode,
+        r_hi, r_lo, ldr, ws.hi, ws.lo, ws.ld, x.data_ptr(), D, row_sum, nrp, xs.aux, g.data_ptr(), B, K, D, mode,
         dx.data_ptr(), D, 0, 0, wsp, wsn, sp()), "dx"), stamps=True)
     timed("GEMM dW+dx fused launch", lambda: chk(L.som_backward_fused(
-        r_hi, r_lo, ldd, xs.hi, xs.lo, ws.hi, ws.lo, xs.ld, x.data_ptr(), D, W.data_ptr(), D, row_sum, nrp, col_sum,
+        r_hi, r_lo, ldr, xs.hi, xs.lo, ws.hi, ws.lo, xs.ld, x.data_ptr(), D, W.data_ptr(), D, row_sum, nrp, col_sum,
         ncp, xs.aux, ws.aux, g.data_ptr(), B, K, D, mode, dw.data_ptr(), D, 0, dx.data_ptr(), D, 0, 0, None, None,
         wsp, wsn, sp()), "bwd"), stamps=True)
     # the fused prototype optimizer step (update + staging): 9 arrays of K x D floats through HBM
@@ -118,9 +128,9 @@ def main():
         W.data_ptr(), D, dw.data_ptr(), D, m.data_ptr(), v.data_ptr(), D, K, D, hp.data_ptr(), 0.9, 0.999, 1e-8, 0.01,
         mode, ws.hi, ws.lo, ws.ld, ws.aux, sp()), "adamw"))
     print(f"   AdamW pass: {9 * K * D * 4 / t_adam / 1e3:.0f} GB/s (9 K D floats; L2-warm)")
-    t_loss = 12.0 * B * K
-    print(f"   (loss kernel moves 12 B per element: {t_loss / 1e6:.1f} MB)")
-    print(f"sum of step kernels: {total:.1f} us  (B={B} K={K} D={D} {fcn}, workspace={'yes' if use_ws else 'no'})")
+    per = 8.0 if f16 else 12.0
+    print(f"   (loss kernel moves {per:.0f} B per element: {per * B * K / 1e6:.1f} MB)")
+    print(f"sum of step kernels: {total:.1f} us  (B={B} K={K} D={D} {fcn} {prec}, workspace={'yes' if use_ws else 'no'})")
 
 
 if __name__ == "__main__":

@@ -583,19 +583,21 @@ __device__ __forceinline__ void split_f16(float v, __half& h, __half& l) {
   h = __float2half_rn(v);
   l = __float2half_rn(v - __half2float(h));
 }
-__device__ __forceinline__ uint2 pack_half4(__half a, __half b, __half c, __half d) {
-  uint2 r;
-  r.x = static_cast<uint32_t>(__half_as_ushort(a)) | (static_cast<uint32_t>(__half_as_ushort(b)) << 16);
-  r.y = static_cast<uint32_t>(__half_as_ushort(c)) | (static_cast<uint32_t>(__half_as_ushort(d)) << 16);
-  return r;
+// two values at a time: one packed conversion each way (cvt.rn.f16x2.f32) instead of scalar conversions and packing
+__device__ __forceinline__ void split2_f16(float a, float b, uint32_t& h, uint32_t& l) {
+  const __half2 hh = __floats2half2_rn(a, b);
+  const float2 f = __half22float2(hh);
+  const __half2 ll = __floats2half2_rn(a - f.x, b - f.y);
+  h = *reinterpret_cast<const uint32_t*>(&hh);
+  l = *reinterpret_cast<const uint32_t*>(&ll);
 }
 // v (already normalised if the mode asks for it) * scale -> hi/lo halves at column i of the staged row
 __device__ __forceinline__ void store_split4_f16(__half* ph, __half* pl, int i, float4 v, float scale) {
-  __half h0, h1, h2, h3, l0, l1, l2, l3;
-  split_f16(v.x * scale, h0, l0); split_f16(v.y * scale, h1, l1);
-  split_f16(v.z * scale, h2, l2); split_f16(v.w * scale, h3, l3);
-  *reinterpret_cast<uint2*>(ph + i) = pack_half4(h0, h1, h2, h3);
-  *reinterpret_cast<uint2*>(pl + i) = pack_half4(l0, l1, l2, l3);
+  uint2 h, l;
+  split2_f16(v.x * scale, v.y * scale, h.x, l.x);
+  split2_f16(v.z * scale, v.w * scale, h.y, l.y);
+  *reinterpret_cast<uint2*>(ph + i) = h;
+  *reinterpret_cast<uint2*>(pl + i) = l;
 }
 
 // GROUP threads cooperate on one row (GROUP = 32: warp per row, GROUP = 256: block per row).

@@ -30,7 +30,7 @@ MODE = {"euclidean": 0, "cosine": 1}
 PREC = {"tf32x3": 0, "fp16x3": 16}
 PREC_FP16X3 = 16
 # what a layer without an explicit ``precision`` attribute computes in (environment override for A/B runs)
-DEFAULT_PRECISION = os.environ.get("SOM_B200_PRECISION", "tf32x3")
+DEFAULT_PRECISION = os.environ.get("SOM_B200_PRECISION", "fp16x3")
 
 
 def is_f16(mode: int) -> bool:
@@ -131,6 +131,14 @@ class Staging:
     def scale_tensor(self) -> torch.Tensor:
         """3xFP16 only: the 2^e row scales."""
         return self.buf[self.aux_off + 2 * self.rows:self.aux_off + 3 * self.rows]
+
+    def dense(self) -> torch.Tensor:
+        """The staged matrix put together again, [rows, ld] fp32 (hi + lo, row scales taken out): what the GEMMs see."""
+        n = self.rows * self.ld
+        if is_f16(self.mode):
+            hi, lo = self.halves()
+            return (hi.float() + lo.float()) / self.scale_tensor()[:, None]
+        return (self.buf[:n] + self.buf[n:2 * n]).view(self.rows, self.ld)
 
     def halves(self):
         """3xFP16 only: (hi, lo) as [rows, ld] fp16 views."""
