@@ -248,8 +248,9 @@ TileChoice pick_tile(int64_t M, int64_t N, int64_t Kred, int sms, int b_mn, int6
       double split_cost = 1e300;
       for (int64_t sp = 2; sp <= split_max && tiles * sp <= workers; ++sp) {
         const int64_t piece = (nkb + sp - 1) / sp;
+        // (two pieces: symmetric hand-over, each pair runs the epilogue on half of the columns)
         const double c = static_cast<double>(piece) * per_kb_ns(2, bn, static_cast<double>(tiles * sp) * 2, panel_loads) +
-                         t_epi + 4000.0 + 2000.0 + HANDOVER_NS * static_cast<double>(sp - 2);
+                         (sp == 2 ? 0.5 * t_epi + 1000.0 : t_epi + 2000.0) + 4000.0 + HANDOVER_NS * static_cast<double>(sp - 2);
         if (c < split_cost) { split_cost = c; split = sp; }
       }
       if (split >= 2) {
