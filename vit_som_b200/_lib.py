@@ -15,7 +15,8 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_uint32, c_void
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libsom_b200.so")
+# (SOM_B200_LIB: an alternative build of the same sources, for A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("SOM_B200_LIB") or os.path.join(_HERE, "libsom_b200.so")
 _SRC = [os.path.join(_HERE, "csrc", "som_b200.cu")]
 _DEPS = _SRC + [os.path.join(_HERE, "csrc", "som_gemm.cuh"), os.path.join(_ROOT, "include", "som_b200.h")]
 

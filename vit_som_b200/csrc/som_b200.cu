@@ -323,7 +323,7 @@ void fill_shape(som::GemmShape& g, const Problem& p, int cg, int bn, int kchunk,
 
 constexpr int kMaxDevices = 64;
 
-template <int EPI>
+template <int EPI, bool F16>
 int launch_single_t(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi,
                     const CUtensorMap& tb_lo, const som::GemmShape& g, const som::EpiParams& e, int grid, size_t smem,
                     cudaStream_t st) {
@@ -332,12 +332,12 @@ int launch_single_t(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CU
   SOM_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= kMaxDevices) return fail(SOM_ERR_DEVICE, "device ordinal out of range");
   if (!attr_set[dev].load(std::memory_order_acquire)) {
-    SOM_CUDA(cudaFuncSetAttribute(som::som_gemm3x_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SOM_CUDA(cudaFuncSetAttribute(som::som_gemm3x_kernel<EPI, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   som::SMEM_LIMIT));
     attr_set[dev].store(true, std::memory_order_release);
   }
-  SOM_CUDA(launch_kernel(som::som_gemm3x_kernel<EPI>, dim3(grid), dim3(som::NUM_THREADS), smem, st, ta_hi, ta_lo, tb_hi,
-                         tb_lo, g, e));
+  SOM_CUDA((launch_kernel(som::som_gemm3x_kernel<EPI, F16>, dim3(grid), dim3(som::NUM_THREADS), smem, st, ta_hi, ta_lo, tb_hi,
+                          tb_lo, g, e)));
   g_launches.fetch_add(1);
   return SOM_OK;
 }
@@ -362,16 +362,17 @@ int resident_pairs(size_t smem, int* out) {
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     int n = 0;
-    SOM_CUDA(cudaFuncSetAttribute(som::som_gemm3x_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  som::SMEM_LIMIT));
-    SOM_CUDA(cudaOccupancyMaxActiveClusters(&n, som::som_gemm3x_pair_kernel<EPI>, &cfg));
+    // (the two precisions of a kernel have the same block size, register limit and shared-memory footprint)
+    SOM_CUDA((cudaFuncSetAttribute(som::som_gemm3x_pair_kernel<EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   som::SMEM_LIMIT)));
+    SOM_CUDA((cudaOccupancyMaxActiveClusters(&n, som::som_gemm3x_pair_kernel<EPI, false>, &cfg)));
     it = cache.emplace(std::make_pair(dev, smem), n).first;
   }
   *out = it->second;
   return SOM_OK;
 }
 
-template <int EPI>
+template <int EPI, bool F16>
 int launch_pair_t(const som::PairMaps& m0, const som::PairMaps& m1, const som::GemmShape& g0, const som::EpiParams& e0,
                   const som::GemmShape& g1, const som::EpiParams& e1, int grid, size_t smem, cudaStream_t st) {
   if (g0.sk_workers > 0) {
@@ -387,12 +388,12 @@ int launch_pair_t(const som::PairMaps& m0, const som::PairMaps& m1, const som::G
   SOM_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= kMaxDevices) return fail(SOM_ERR_DEVICE, "device ordinal out of range");
   if (!attr_set[dev].load(std::memory_order_acquire)) {
-    SOM_CUDA(cudaFuncSetAttribute(som::som_gemm3x_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  som::SMEM_LIMIT));
+    SOM_CUDA((cudaFuncSetAttribute(som::som_gemm3x_pair_kernel<EPI, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   som::SMEM_LIMIT)));
     attr_set[dev].store(true, std::memory_order_release);
   }
-  SOM_CUDA(launch_kernel(som::som_gemm3x_pair_kernel<EPI>, dim3(grid), dim3(som::NUM_THREADS_2CTA), smem, st, m0, m1, g0,
-                         e0, g1, e1));
+  SOM_CUDA((launch_kernel(som::som_gemm3x_pair_kernel<EPI, F16>, dim3(grid), dim3(som::NUM_THREADS_2CTA), smem, st, m0, m1, g0,
+                          e0, g1, e1)));
   g_launches.fetch_add(1);
   return SOM_OK;
 }
@@ -463,10 +464,18 @@ int launch_pair(int epi, const Problem* probs, int nprob, int bn, int sk_workers
   const int grid = g[0].sk_workers > 0 ? g[0].sk_workers * 2 : static_cast<int>(nwork < slots ? nwork : slots) * 2;
   som::EpiParams e0 = probs[0].e, e1 = probs[nprob - 1].e;
   e0.dbg = e1.dbg = g_debug.load();
-  switch (epi) {
-    case som::EPI_RAW:  return launch_pair_t<som::EPI_RAW>(maps[0], maps[1], g[0], e0, g[1], e1, grid, smem, st);
-    case som::EPI_DIST: return launch_pair_t<som::EPI_DIST>(maps[0], maps[1], g[0], e0, g[1], e1, grid, smem, st);
-    case som::EPI_GRAD: return launch_pair_t<som::EPI_GRAD>(maps[0], maps[1], g[0], e0, g[1], e1, grid, smem, st);
+  if (f16) {
+    switch (epi) {
+      case som::EPI_RAW:  return launch_pair_t<som::EPI_RAW, true>(maps[0], maps[1], g[0], e0, g[1], e1, grid, smem, st);
+      case som::EPI_DIST: return launch_pair_t<som::EPI_DIST, true>(maps[0], maps[1], g[0], e0, g[1], e1, grid, smem, st);
+      case som::EPI_GRAD: return launch_pair_t<som::EPI_GRAD, true>(maps[0], maps[1], g[0], e0, g[1], e1, grid, smem, st);
+    }
+  } else {
+    switch (epi) {
+      case som::EPI_RAW:  return launch_pair_t<som::EPI_RAW, false>(maps[0], maps[1], g[0], e0, g[1], e1, grid, smem, st);
+      case som::EPI_DIST: return launch_pair_t<som::EPI_DIST, false>(maps[0], maps[1], g[0], e0, g[1], e1, grid, smem, st);
+      case som::EPI_GRAD: return launch_pair_t<som::EPI_GRAD, false>(maps[0], maps[1], g[0], e0, g[1], e1, grid, smem, st);
+    }
   }
   return fail(SOM_ERR_ARG, "unknown epilogue");
 }
@@ -519,10 +528,18 @@ int launch_gemm(int epi, const float* a_hi, const float* a_lo, int64_t lda, int 
   if (int rc = make_problem_maps(p, som::BM, bn, &ta_hi, &ta_lo, &tb_hi, &tb_lo)) return rc;
   const int64_t nwork = static_cast<int64_t>(g.tiles_m) * g.tiles_n;
   const int grid = static_cast<int>(nwork < sms ? nwork : sms);
-  switch (epi) {
-    case som::EPI_RAW:  return launch_single_t<som::EPI_RAW>(ta_hi, ta_lo, tb_hi, tb_lo, g, e, grid, smem, st);
-    case som::EPI_DIST: return launch_single_t<som::EPI_DIST>(ta_hi, ta_lo, tb_hi, tb_lo, g, e, grid, smem, st);
-    case som::EPI_GRAD: return launch_single_t<som::EPI_GRAD>(ta_hi, ta_lo, tb_hi, tb_lo, g, e, grid, smem, st);
+  if (f16) {
+    switch (epi) {
+      case som::EPI_RAW:  return launch_single_t<som::EPI_RAW, true>(ta_hi, ta_lo, tb_hi, tb_lo, g, e, grid, smem, st);
+      case som::EPI_DIST: return launch_single_t<som::EPI_DIST, true>(ta_hi, ta_lo, tb_hi, tb_lo, g, e, grid, smem, st);
+      case som::EPI_GRAD: return launch_single_t<som::EPI_GRAD, true>(ta_hi, ta_lo, tb_hi, tb_lo, g, e, grid, smem, st);
+    }
+  } else {
+    switch (epi) {
+      case som::EPI_RAW:  return launch_single_t<som::EPI_RAW, false>(ta_hi, ta_lo, tb_hi, tb_lo, g, e, grid, smem, st);
+      case som::EPI_DIST: return launch_single_t<som::EPI_DIST, false>(ta_hi, ta_lo, tb_hi, tb_lo, g, e, grid, smem, st);
+      case som::EPI_GRAD: return launch_single_t<som::EPI_GRAD, false>(ta_hi, ta_lo, tb_hi, tb_lo, g, e, grid, smem, st);
+    }
   }
   return fail(SOM_ERR_ARG, "unknown epilogue");
 }
