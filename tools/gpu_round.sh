@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round evidence on the GPU box:  gpurun -- 'bash tools/gpu_round.sh <tag> [stage ...]'
-# stages: smoke tests bench steptime small ncu   (default: all but ncu)
+# stages: smoke tests bench steptime small tf32 ncu   (default: all but tf32 and ncu)
 set -u
 TAG=${1:-r02a}; shift || true
 STAGES=${*:-smoke tests bench steptime small}
@@ -17,7 +17,12 @@ if has bench; then
 fi
 if has steptime; then
   timeout 300 python tools/step_time.py > gpurun_out/steptime_cfg2_${TAG}.log 2>&1; cat gpurun_out/steptime_cfg2_${TAG}.log
-  timeout 300 python tools/step_time.py 4096 128 128 256 > gpurun_out/steptime_cfg5_${TAG}.log 2>&1; cat gpurun_out/steptime_cfg5_${TAG}.log
+  timeout 300 python tools/step_time.py 1024 40 40 3136 euclidean tf32x3 > gpurun_out/steptime_cfg2_tf32_${TAG}.log 2>&1; grep -E "GEMM|sum" gpurun_out/steptime_cfg2_tf32_${TAG}.log
+  timeout 300 python tools/step_time.py 8192 128 128 256 > gpurun_out/steptime_cfg5chunk_${TAG}.log 2>&1; cat gpurun_out/steptime_cfg5chunk_${TAG}.log
+  timeout 300 python tools/step_time.py 128 4 4 12288 cosine > gpurun_out/steptime_cfg3_${TAG}.log 2>&1
+fi
+if has tf32; then
+  timeout 600 python bench.py --precision tf32x3 --no-vit --no-cpu-baseline > gpurun_out/bench_tf32_${TAG}.json 2> gpurun_out/bench_tf32_${TAG}.err; echo "bench tf32x3 rc=$?"; tail -c 1500 gpurun_out/bench_tf32_${TAG}.json
 fi
 if has small; then
   for w in cfg1 cfg3 cfg4; do
@@ -30,7 +35,7 @@ if has ncu; then
   ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv $SHORT > gpurun_out/ncu_list_${TAG}.log 2>&1
   echo "ncu list rc=$?"
   $SHORT > gpurun_out/plain2_${TAG}.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k 'regex:som_gemm3x|loss_coeffs|prep_rows|adamw' -s 16 -c 6 -f -o gpurun_out/prof_${TAG} $SHORT > gpurun_out/ncu_full_${TAG}.log 2>&1
+  ncu --set full --clock-control none --import-source on -k 'regex:som_gemm3x|loss_coeffs|prep_rows|bmu_decode' -s 20 -c 5 -f -o gpurun_out/prof_${TAG} $SHORT > gpurun_out/ncu_full_${TAG}.log 2>&1
   echo "ncu full rc=$?"
 fi
 ls -la gpurun_out | tail -8

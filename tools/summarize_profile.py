@@ -1,11 +1,11 @@
 """Turn the ncu artefacts gpurun brought back (gpurun_out/) into the committed text summaries under profiles/.
 
-    python tools/summarize_profile.py <tag> [--workload cfg2]
+    python tools/summarize_profile.py <tag> [--workload cfg2] [--precision fp16x3|tf32x3]
 
 Inputs : gpurun_out/launches_<tag>.csv   (ncu --metrics gpu__time_duration.sum launch list)
          gpurun_out/prof_<tag>.ncu-rep   (ncu --set full capture of the hot kernels)
 Outputs: profiles/<tag>_launches.txt, profiles/<tag>_ncu_kernels.txt, profiles/traffic_r02.json (per-launch DRAM
-         bytes of the tensor-core GEMM, keyed "<workload>@n<GPUs>", read by bench.py for roofline.traffic)
+         bytes of the tensor-core GEMM, keyed "<workload>@n<GPUs>[@fp16x3]", read by bench.py for roofline.traffic)
 """
 import csv
 import json
@@ -99,11 +99,37 @@ def kernels(tag, out, workload):
                 cur = json.load(f)
         # one step = one launch of each GEMM kernel (forward, fused backward): average over the kinds
         per_kind = {k: sum(v) / len(v) for k, v in gemm_traffic.items()}
-        cur[f"{workload}@n1"] = {"dram_bytes_per_launch": sum(per_kind.values()) / len(per_kind),
+        precision = sys.argv[sys.argv.index("--precision") + 1] if "--precision" in sys.argv else "fp16x3"
+        key = f"{workload}@n1" + ("" if precision == "tf32x3" else f"@{precision}")
+        cur[key] = {"dram_bytes_per_launch": sum(per_kind.values()) / len(per_kind),
                          "per_kernel": per_kind, "note": "ncu --set full, cold L2 (flushed before every replay pass)",
                          "source": f"profiles/{tag}_ncu_kernels.txt"}
         with open(tpath, "w") as f:
             json.dump(cur, f, indent=1)
+
+
+def loss_kernel(tag, out):
+    """Full capture of the fused loss kernel at a config-5 chunk (gpurun_out/prof_loss_cfg5_<tag>.ncu-rep), appended."""
+    rep = os.path.join(ROOT, "gpurun_out", f"prof_loss_cfg5_{tag}.ncu-rep")
+    if not os.path.exists(rep):
+        return
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    if len(rows) < 3:
+        return
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    idx = {h: i for i, h in enumerate(hdr)}
+    extra = [("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy %"),
+             ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall: long scoreboard"),
+             ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall: short scoreboard"),
+             ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "stall: wait")]
+    with open(out, "a") as f:
+        f.write("\n# the fused loss kernel at a config-5 chunk (8192 x 16384), python tools/step_time.py 8192 128 128 256\n")
+        for d in data:
+            f.write(f"\n== {short(d[idx['Kernel Name']])}  grid {d[idx['Grid Size']]} block {d[idx['Block Size']]}\n")
+            for m, label in METRICS + extra:
+                if m in idx:
+                    f.write(f"   {label:24s} {d[idx[m]]:>14s} {units[idx[m]]}\n")
 
 
 def main():
@@ -112,6 +138,7 @@ def main():
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     launches(tag, os.path.join(ROOT, "profiles", f"{tag}_launches.txt"))
     kernels(tag, os.path.join(ROOT, "profiles", f"{tag}_ncu_kernels.txt"), workload)
+    loss_kernel(tag, os.path.join(ROOT, "profiles", f"{tag}_ncu_kernels.txt"))
 
 
 if __name__ == "__main__":
