@@ -1,9 +1,14 @@
 // som_b200.cu — C-ABI library of the B200-native SOM-layer hot path (see include/som_b200.h).
 //
 // Kernels in this translation unit (all sm_100a):
-//   som_gemm3x_kernel<EPI_DIST|EPI_GRAD|EPI_RAW>  tcgen05/TMA 3xTF32 GEMM + fused epilogue (som_gemm.cuh)
-//   prep_rows_kernel        operand staging: row norms (+ F.normalize) and exact tf32 hi/lo split
-//   bmu_init/decode         packed (key,index) <-> int64 BMU
+//   som_gemm3x_pair_kernel / som_gemm3x_kernel <EPI_DIST|EPI_GRAD|EPI_RAW, F16>
+//                           tcgen05/TMA GEMM in 3xFP16 or 3xTF32 + fused epilogue (som_gemm.cuh)
+//   prep_rows_kernel        operand staging: row norms (+ F.normalize) and the hi/lo split (row-scaled fp16, or tf32)
+//   bmu_init/decode         packed (key,index) <-> int64 BMU; bmu_decode_stat_kernel also leaves the batch statistic
+//                           that scales the fp16 backward operand
+//   loss_coeffs_*_kernel    fused loss + backward staging (R hi/lo, partial row / column sums)
+//   adamw_stage_kernel      prototype AdamW step + staging of the new prototypes
+//   nvls_allreduce_mean_kernel  two-shot NVLS all-reduce of the multi-GPU exchanges
 //   neighbourhood_kernel    Gaussian grid weights, materialised on demand     (models/som_layer.py:144-152)
 //   weighted_loss_kernel    mean(w * d) with w recomputed in registers        (models/som_layer.py:137-142)
 //   loss_grad_kernel        G = g_out * w / (B K)
