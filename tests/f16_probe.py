@@ -1,4 +1,4 @@
-"""GPU probe of the 3xFP16 path (run through gpurun): GEMM mainloop in every operand layout against fp64, accuracy next
+"""GPU probe of the 3xFP16 path (run through gpurun; lives under tests/ because it uses the oracle as its checker): GEMM mainloop in every operand layout against fp64, accuracy next
 to 3xTF32 on the same data, timings of the three GEMM shapes of config 2 / a config-5 chunk, then the layer end to end
 (forward, loss, backward) against the fp64 oracle in both precisions."""
 import ctypes
