@@ -236,6 +236,10 @@ int som_loss_fused(const float* dist, int64_t ldd, const int64_t* bmu, const flo
  * euclidean: c = sum of the row's parts, s = 1;  cosine: c = aux^2 * sum, s = aux.  accumulate != 0 adds into the
  * output (row-chunked batches accumulate dW across chunks).  sm_limit > 0: the launch occupies at most that many SMs
  * (the caller runs a collective kernel beside it); 0 = all.
+ * SOM_PREC_FP16X3: r_hi / r_lo hold the scaled R^ of som_loss_fused and the staged operands their row-scaled fp16 split;
+ * the epilogue multiplies s of output row m by 2^e_m (x_aux[2 B + m] for dx, w_aux[2 K + m] for dW) and by 1 / S
+ * (row_part[B * n_row_parts] for dx, col_part[n_col_parts * K] for dW), so dW / dx come out unscaled; x_aux / w_aux are
+ * then required for both distance modes.
  */
 int som_backward_dw(const float* r_hi, const float* r_lo, int64_t ldr,
                     const float* x_hi, const float* x_lo, int64_t ld_stage,
